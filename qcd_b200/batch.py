@@ -1,0 +1,184 @@
+"""EnvBatch: N CircuitDesigner environments resident in HBM + the launches of libqcd_b200.so.
+
+Owns every device buffer named in `qcd_batch_t` (include/qcd_b200.h) as a torch tensor, so the
+kernels never allocate; torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import QcdBatch, QcdTapeOut, check
+
+
+def objective_kind(objective: str) -> int:
+  """'SP-…' -> OBJ_SP, 'UC-…' -> OBJ_UC (the reference tests `'UC' in objective`, env.py:82-84)."""
+  if 'UC' in objective:
+    return _lib.OBJ_UC
+  if 'SP' in objective:
+    return _lib.OBJ_SP
+  raise AssertionError(f'{objective} not defined.')
+
+
+def _ptr(t):
+  return None if t is None else t.data_ptr()
+
+
+class EnvBatch:
+  """Device-resident state of `num_envs` environments with a common (eta, delta, objective).
+
+  target: complex128 numpy/torch array, [S-shaped] shared or [N, S-shaped] per env.
+  obs_mode: 'full'  -> obs rows are the reference observation [state | target] (4*S floats; the target
+                       half is written once here and never touched by the kernels),
+            'state' -> rows hold only the state half (2*S floats), 'none' -> no observations.
+  """
+
+  def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str, target,
+               punish: bool = True, sparse: bool = True, autoreset: bool = True, obs_mode: str = 'full',
+               final_obs: bool = False, track_episodes: bool = True, device=None):
+    if not torch.cuda.is_available():
+      raise RuntimeError("qcd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    self.lib = _lib.load_library()
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    self.kind = objective_kind(objective)
+    if not 1 <= max_qubits <= _lib.MAX_QUBITS[self.kind]:
+      raise ValueError(f"max_qubits={max_qubits} outside 1..{_lib.MAX_QUBITS[self.kind]} for {objective}")
+    if not 1 <= max_depth <= _lib.MAX_DEPTH:
+      raise ValueError(f"max_depth={max_depth} outside 1..{_lib.MAX_DEPTH}")
+    if obs_mode not in ('full', 'state', 'none'):
+      raise ValueError(obs_mode)
+    self.num_envs, self.qubits, self.max_depth, self.objective = int(num_envs), int(max_qubits), int(max_depth), objective
+    self.punish, self.sparse, self.autoreset, self.obs_mode = bool(punish), bool(sparse), bool(autoreset), obs_mode
+    self.dim = 2 ** self.qubits
+    self.S = self.dim if self.kind == _lib.OBJ_SP else self.dim * self.dim
+    N, S, dev = self.num_envs, self.S, self.device
+
+    tgt = torch.as_tensor(np.asarray(target) if not torch.is_tensor(target) else target).to(torch.complex128)
+    if tgt.numel() == S:
+      self.per_env_target = False
+      tgt = tgt.reshape(S)
+    elif tgt.numel() == N * S:
+      self.per_env_target = True
+      tgt = tgt.reshape(N, S)
+    else:                     # e.g. SP-ghz3 on 4 qubits: the reference fails inside np.vdot (env.py:109)
+      raise ValueError(f"target has {tgt.numel()} amplitudes, the state has {S}")
+    self.target = tgt.contiguous().to(dev)
+
+    f64, i32, u8 = torch.float64, torch.int32, torch.uint8
+    self.state = torch.zeros((N, S), dtype=torch.complex128, device=dev)
+    self.meta = torch.zeros((N, 16), dtype=u8, device=dev)
+    self.last = torch.zeros((N, 2), dtype=f64, device=dev)
+    self.ep_return = torch.zeros(N, dtype=f64, device=dev) if track_episodes else None
+    self.ep_length = torch.zeros(N, dtype=i32, device=dev) if track_episodes else None
+    self.episode_return = torch.zeros(N, dtype=f64, device=dev) if track_episodes else None
+    self.episode_length = torch.zeros(N, dtype=i32, device=dev) if track_episodes else None
+    self.reward = torch.zeros(N, dtype=f64, device=dev)
+    self.metric = torch.zeros(N, dtype=f64, device=dev)
+    self.cost = torch.zeros(N, dtype=f64, device=dev)
+    self.depth = torch.zeros(N, dtype=i32, device=dev)
+    self.operations = torch.zeros(N, dtype=i32, device=dev)
+    self.used_wires = torch.zeros(N, dtype=i32, device=dev)
+    self.terminated = torch.zeros(N, dtype=u8, device=dev)
+    self.truncated = torch.zeros(N, dtype=u8, device=dev)
+    self.status = torch.zeros(N, dtype=torch.int8, device=dev)
+    self.stats = torch.zeros(_lib.STATS_LEN, dtype=f64, device=dev)
+
+    self.obs = self.final_obs = None
+    self.obs_stride = 2 * S
+    if obs_mode != 'none':
+      self.obs_stride = 4 * S if obs_mode == 'full' else 2 * S
+      self.obs = torch.zeros((N, self.obs_stride), dtype=torch.float32, device=dev)
+      if final_obs:
+        self.final_obs = torch.zeros((N, self.obs_stride), dtype=torch.float32, device=dev)
+      if obs_mode == 'full':                      # constant half: flat(target) (env.py:85)
+        tflat = torch.cat([self.target.real, self.target.imag], dim=-1).to(torch.float32)
+        self.obs[:, 2 * S:] = tflat
+        if self.final_obs is not None:
+          self.final_obs[:, 2 * S:] = tflat
+
+    flags = (_lib.F_PUNISH if self.punish else 0) | (_lib.F_SPARSE if self.sparse else 0) | \
+            (_lib.F_AUTORESET if self.autoreset else 0) | (_lib.F_TARGET_PER_ENV if self.per_env_target else 0)
+    d = self.max_depth
+    self.c = QcdBatch(
+        n_envs=N, n_qubits=self.qubits, objective=self.kind, max_depth=d, flags=flags, reserved0=0,
+        depth_free=d / 3, cost_denom=d / 2 * 3,         # env.py:112, evaluated in Python float64
+        obs_stride=self.obs_stride,
+        state=_ptr(self.state), target=_ptr(self.target), meta=_ptr(self.meta), last=_ptr(self.last),
+        ep_return=_ptr(self.ep_return), ep_length=_ptr(self.ep_length),
+        obs=_ptr(self.obs), final_obs=_ptr(self.final_obs),
+        reward=_ptr(self.reward), metric=_ptr(self.metric), cost=_ptr(self.cost),
+        depth=_ptr(self.depth), operations=_ptr(self.operations), used_wires=_ptr(self.used_wires),
+        terminated=_ptr(self.terminated), truncated=_ptr(self.truncated), status=_ptr(self.status),
+        episode_return=_ptr(self.episode_return), episode_length=_ptr(self.episode_length))
+    self._cref = C.byref(self.c)
+    self.reset()
+
+  # ------------------------------------------------------------------------------------------
+  def _stream(self):
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def _action_arg(self, actions: torch.Tensor, lead: tuple):
+    if not torch.is_tensor(actions):
+      raise TypeError("actions must be a torch tensor on the env's device (use step_host for host arrays)")
+    if actions.device != self.device:
+      raise ValueError(f"actions live on {actions.device}, the envs on {self.device}")
+    if tuple(actions.shape) != lead + (self.num_envs, 4):
+      raise ValueError(f"actions must have shape {lead + (self.num_envs, 4)}, got {tuple(actions.shape)}")
+    if actions.dtype == torch.float32:
+      code = _lib.ACT_F32
+    elif actions.dtype == torch.float64:
+      code = _lib.ACT_F64
+    else:
+      raise TypeError(f"actions must be float32 or float64, got {actions.dtype}")
+    if not actions.is_contiguous():
+      actions = actions.contiguous()
+    return actions, code
+
+  def reset(self, mask: torch.Tensor | None = None) -> None:
+    """env.py:117-121 for all envs, or those with mask != 0 (uint8 [N] on device)."""
+    if mask is not None:
+      mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+    with torch.cuda.device(self.device):
+      check(self.lib.qcd_reset(self._cref, _ptr(mask), self._stream()), "qcd_reset")
+
+  def step(self, actions: torch.Tensor) -> None:
+    """One env.step for every env (env.py:124-136); results land in the output tensors."""
+    actions, code = self._action_arg(actions, ())
+    with torch.cuda.device(self.device):
+      check(self.lib.qcd_step(self._cref, actions.data_ptr(), code, self._stream()), "qcd_step")
+
+  def replay(self, tape: torch.Tensor, record: dict | None = None) -> None:
+    """T fused steps with the states resident in shared memory.  tape: [T,N,4] on device.
+    record: optional dict of preallocated [T,N] tensors keyed by reward/metric/cost/depth/
+    terminated/truncated/status."""
+    tape, code = self._action_arg(tape, (int(tape.shape[0]),))
+    out = QcdTapeOut()
+    want = {'reward': torch.float64, 'metric': torch.float64, 'cost': torch.float64, 'depth': torch.int32,
+            'terminated': torch.uint8, 'truncated': torch.uint8, 'status': torch.int8}
+    for key, t in (record or {}).items():
+      if key not in want:
+        raise KeyError(key)
+      if t.dtype != want[key] or tuple(t.shape) != (tape.shape[0], self.num_envs) or not t.is_contiguous() \
+          or t.device != self.device:
+        raise ValueError(f"record[{key!r}] must be a contiguous {want[key]} [T,N] tensor on {self.device}")
+      setattr(out, key, t.data_ptr())
+    with torch.cuda.device(self.device):
+      check(self.lib.qcd_replay(self._cref, tape.data_ptr(), code, int(tape.shape[0]), C.byref(out),
+                                self._stream()), "qcd_replay")
+
+  def reduce_stats(self) -> None:
+    """Add the finished-episode statistics of the last step to `self.stats`."""
+    with torch.cuda.device(self.device):
+      check(self.lib.qcd_reduce_stats(self._cref, self.stats.data_ptr(), self._stream()), "qcd_reduce_stats")
+
+  # ------------------------------------------------------------------------------------------
+  def state_view(self) -> torch.Tensor:
+    """complex128 [N,D] (SP) or [N,D,D] (UC) view of the resident states."""
+    return self.state if self.kind == _lib.OBJ_SP else self.state.view(self.num_envs, self.dim, self.dim)
+
+  def algorithmic_bytes_per_step(self) -> int:
+    """32*S state r/w + 8*S float32 observation + 96 B scalars."""
+    return 32 * self.S + (8 * self.S if self.obs is not None else 0) + 96

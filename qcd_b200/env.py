@@ -1,0 +1,110 @@
+"""CircuitDesigner — the reference's single-environment gymnasium API on the B200 batch engine.
+
+Drop-in for /root/reference/qcd_gym/env.py:13-141: same constructor kwargs, attributes, spaces,
+`reset` / `step` / `render` signatures, observation layout, info keys and exceptions.  The state
+lives on the GPU as an `EnvBatch` of one env (autoreset off); every `step` is one `qcd_step`
+launch followed by a read-back of the observation and the scalars.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batch import EnvBatch
+from .gym_compat import Box, Env, np_random
+from .targets import make_target
+from .vector_env import GATES, action_space_for
+
+
+class CircuitDesigner(Env):
+  """ Quantum Circuit Environment: build a quantum circuit gate-by-gate for a desired objective.
+
+  Attributes (env.py:16-20): qubits, depth, objective, punish; plus max_steps, sparse, target, name.
+  """
+
+  metadata = {"render_modes": ["image", "text"], "render_fps": 30}
+
+  def __init__(self, max_qubits: int, max_depth: int, objective: str,
+               punish=True, sparse=True, seed=None, render_mode=None, device=None):
+    super().__init__()
+    if seed is not None: self._np_random, seed = np_random(seed)                  # env.py:32
+    self.render_mode = render_mode; self.name = f"{objective}|{max_qubits}-{max_depth}"
+    self.qubits, self.depth = max_qubits, max_depth
+    self.max_steps = max_depth * max_qubits * 2                                   # env.py:37
+    self.punish = punish; self.sparse = sparse
+    self.objective = objective
+    self.target = make_target(objective, max_qubits, seed)                        # env.py:40
+    self._batch = EnvBatch(1, max_qubits, max_depth, objective, self.target, punish=punish, sparse=sparse,
+                           autoreset=False, obs_mode='full', track_episodes=False, device=device)
+    self._ops = []                         # host mirror of the circuit, used by render() only
+    b = self._batch
+    self._action_dev = torch.zeros((1, 4), dtype=torch.float64, device=b.device)
+    self._action_host = torch.zeros((1, 4), dtype=torch.float64, pin_memory=True)
+    self.observation_space = Box(low=-1.0, high=+1.0, shape=(4 * b.S,))           # env.py:44
+    self.action_space = action_space_for(self.qubits)                             # env.py:46-49
+
+  # ------------------------------------------------------------------------------------------
+  def _read(self):
+    b = self._batch
+    obs = b.obs[0].cpu().numpy()
+    info = {'depth': int(b.depth[0]), 'operations': int(b.operations[0]), 'used_wires': int(b.used_wires[0])}
+    return obs, info
+
+  def _operation(self, action):
+    """env.py:90-100: host-side replica of the decode, for the exceptions and for render()."""
+    gate, wire, cntrl, theta = action
+    gate, wire, cntrl = np.floor([gate, wire, cntrl]).astype(int)
+    assert wire in range(self.qubits) and cntrl in range(self.qubits), f"{action}"
+    if wire == cntrl and gate == 0: return ('p', [wire], float(theta))
+    if wire == cntrl and gate == 1: return ('rx', [wire], float(theta))
+    if gate == 0: return ('cp', [cntrl, wire], float(theta))
+    if gate == 1: return ('cx', [cntrl, wire], None)
+    if gate == 2: return None
+    assert False, f'Unhandled Action on gate {gate}'
+
+  def reset(self, seed=None, options=None):
+    super().reset(seed=seed)
+    self._batch.reset()
+    self._ops = []
+    return self._read()
+
+  def step(self, action):
+    operation = self._operation(action)              # raises AssertionError like env.py:94,100
+    if operation is not None: self._ops.append(operation)
+    self._action_host[0] = torch.as_tensor(np.asarray(action, dtype=np.float64))
+    self._action_dev.copy_(self._action_host, non_blocking=True)
+    b = self._batch
+    b.step(self._action_dev)
+    state, info = self._read()
+    terminated, truncated = bool(b.terminated[0]), bool(b.truncated[0])
+    if terminated: info['termination_reason'] = 'DONE'
+    if truncated: info['termination_reason'] = 'DEPTH'                            # env.py:130-131
+    info = {**info, 'metric': float(b.metric[0]), 'cost': float(b.cost[0])}
+    return state, float(b.reward[0]), terminated, truncated, info
+
+  # ------------------------------------------------------------------------------------------
+  def render(self):
+    """Text drawing of the circuit built so far (the reference delegates to qiskit's drawer,
+    env.py:139-141; 'image' needs matplotlib+qiskit and is not available here)."""
+    if self.render_mode is None: return None
+    if self.render_mode != 'text':
+      raise NotImplementedError("render_mode='image' needs qiskit's matplotlib drawer")
+    rows = [[f"q_{q}: "] for q in range(self.qubits)]
+    for kind, qargs, theta in self._ops:
+      label = {'p': 'P', 'rx': 'Rx', 'cp': 'P', 'cx': 'X'}[kind] + ('' if theta is None else f"({theta:.3g})")
+      width = len(label) + 2
+      tgt = qargs[-1]
+      ctl = qargs[0] if len(qargs) == 2 else None
+      lo, hi = (min(qargs), max(qargs))
+      for q in range(self.qubits):
+        if q == tgt: cell = label.center(width, '─')
+        elif q == ctl: cell = '■'.center(width, '─')
+        elif lo < q < hi: cell = '│'.center(width, '─')
+        else: cell = '─' * width
+        rows[q].append(cell)
+    return '\n'.join(''.join(r) for r in rows)
+
+  @property
+  def state(self) -> np.ndarray:
+    """complex128 state vector / unitary currently resident on the device."""
+    return self._batch.state_view()[0].cpu().numpy()

@@ -1,0 +1,161 @@
+"""CircuitDesignerVectorEnv — N reference environments stepped by one kernel launch.
+
+Replaces the SB3 `DummyVecEnv([Monitor(gym.make(...))] * n)` loop of
+/root/reference/algorithm/algorithm.py:25-27 (sequential Python, one qiskit re-simulation per env
+per step) behind the same constructor kwargs as `CircuitDesigner` (env.py:29-30).
+
+Semantics: gymnasium-0.29 VectorEnv same-step auto-reset.  When env i finishes, `reward[i]`,
+`terminated[i]`, `truncated[i]` and the info tensors describe the finished step, `obs[i]` is already
+the first observation of the next episode, `info['final_observation']` (if enabled) holds the
+terminal one, and `info['episode']` carries Monitor's r/l (monitor.py:37-38); d/o/q/m/c of
+monitor.py:44-48 are the info tensors depth/operations/used_wires/metric/cost at the same index.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .batch import EnvBatch
+from .gym_compat import Box, np_random
+from .targets import make_target
+
+GATES = 3
+
+
+def action_space_for(qubits: int) -> Box:
+  """env.py:46-49 — Box([0,0,0,-pi], [3-m, eta-m, eta-m, pi]) in float32."""
+  m = 1e-5
+  return Box(np.array([0, 0, 0, -np.pi]), np.array([GATES - m, qubits - m, qubits - m, np.pi]))
+
+
+class CircuitDesignerVectorEnv:
+  metadata = {"render_modes": [], "autoreset_mode": "same_step"}
+
+  def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str,
+               punish=True, sparse=True, seed=None, target=None, device=None,
+               obs_mode: str = 'full', final_obs: bool = False, autoreset: bool = True,
+               raise_on_invalid: bool = False):
+    self.num_envs = int(num_envs)
+    self.qubits, self.depth = max_qubits, max_depth
+    self.max_steps = max_depth * max_qubits * 2
+    self.punish, self.sparse, self.objective = punish, sparse, objective
+    self.name = f"{objective}|{max_qubits}-{max_depth}"
+    self.raise_on_invalid = raise_on_invalid
+    self._np_random = None
+    if seed is not None:
+      self._np_random, seed = np_random(seed)
+    # env.py:40 — one target for the lifetime of the env; DummyVecEnv gives every env the same seed
+    # and therefore the same target (algorithm.py:25-27), which is the `shared` layout here.
+    self.target = make_target(objective, max_qubits, seed) if target is None else target
+    self.batch = EnvBatch(self.num_envs, max_qubits, max_depth, objective, self.target, punish=punish,
+                          sparse=sparse, autoreset=autoreset, obs_mode=obs_mode, final_obs=final_obs,
+                          device=device)
+    self.device = self.batch.device
+    S = self.batch.S
+    self.single_observation_space = Box(low=-1.0, high=+1.0, shape=(4 * S,))
+    self.single_action_space = action_space_for(max_qubits)
+    self.observation_space = Box(low=-1.0, high=+1.0, shape=(self.num_envs, self.batch.obs_stride))
+    self.action_space = Box(np.tile(self.single_action_space.low, (self.num_envs, 1)),
+                            np.tile(self.single_action_space.high, (self.num_envs, 1)))
+    self._host = None
+
+  # ------------------------------------------------------------------------------------------
+  def _info(self) -> dict:
+    b = self.batch
+    info = {'depth': b.depth, 'operations': b.operations, 'used_wires': b.used_wires,
+            'metric': b.metric, 'cost': b.cost, 'status': b.status}
+    if b.episode_return is not None:
+      info['episode'] = {'r': b.episode_return, 'l': b.episode_length}
+    if b.final_obs is not None:
+      info['final_observation'] = b.final_obs
+    return info
+
+  def reset(self, *, seed=None, options=None):
+    if seed is not None:
+      self._np_random, _ = np_random(seed)
+    self.batch.reset()
+    b = self.batch
+    return b.obs, {'depth': b.depth, 'operations': b.operations, 'used_wires': b.used_wires}
+
+  def step(self, actions: torch.Tensor):
+    """actions: float32/float64 [N,4] tensor on the env's device.  Returns persistent device
+    tensors (no allocation, no synchronisation): obs, reward f64, terminated, truncated, info."""
+    b = self.batch
+    b.step(actions)
+    if self.raise_on_invalid and bool((b.status != 0).any()):
+      bad = int(torch.nonzero(b.status)[0])
+      raise AssertionError(f"env {bad}: invalid action {actions[bad].tolist()} (status {int(b.status[bad])})")
+    return b.obs, b.reward, b.terminated.view(torch.bool), b.truncated.view(torch.bool), self._info()
+
+  def replay(self, tape: torch.Tensor, record: dict | None = None):
+    """Apply a whole action tape [T,N,4] in one launch (states stay in shared memory)."""
+    b = self.batch
+    b.replay(tape, record)
+    return b.obs, b.reward, b.terminated.view(torch.bool), b.truncated.view(torch.bool), self._info()
+
+  # ------------------------------------------------------------------------------------------
+  def _host_buffers(self, action_dtype):
+    if self._host is None or self._host['actions'].dtype != action_dtype:
+      N, b = self.num_envs, self.batch
+      pin = dict(pin_memory=True)
+      host = {
+          'actions': torch.zeros((N, 4), dtype=action_dtype, **pin),
+          'actions_dev': torch.zeros((N, 4), dtype=action_dtype, device=self.device),
+          'reward': torch.zeros(N, dtype=torch.float64, **pin),
+          'terminated': torch.zeros(N, dtype=torch.uint8, **pin),
+          'truncated': torch.zeros(N, dtype=torch.uint8, **pin),
+          'obs': None,
+      }
+      if b.obs is not None:
+        host['obs'] = torch.zeros((N, b.obs_stride), dtype=torch.float32, **pin)
+        if b.obs_mode == 'full':
+          host['obs'][:, 2 * b.S:] = b.obs[0, 2 * b.S:].cpu()
+      self._host = host
+    return self._host
+
+  def step_host(self, actions, copy_obs: bool = True):
+    """The end-to-end call with HOST buffers: numpy actions in, numpy results out.
+
+    H2D copy of the actions, the step kernel and the D2H copies of reward / terminated / truncated
+    (and the state half of every observation row) are issued on the current stream by
+    `qcd_step_host`, followed by one stream synchronisation.  Returned arrays are views of pinned
+    host buffers that the next call overwrites."""
+    a = np.asarray(actions)
+    dt = torch.float64 if a.dtype == np.float64 else torch.float32
+    h = self._host_buffers(dt)
+    h['actions'].numpy()[...] = a.reshape(self.num_envs, 4)
+    b = self.batch
+    obs_h = h['obs'] if (copy_obs and h['obs'] is not None) else None
+    stream = torch.cuda.current_stream(self.device)
+    with torch.cuda.device(self.device):
+      _lib.check(b.lib.qcd_step_host(
+          b._cref, h['actions'].data_ptr(), h['actions_dev'].data_ptr(),
+          _lib.ACT_F64 if dt == torch.float64 else _lib.ACT_F32,
+          h['reward'].data_ptr(), h['terminated'].data_ptr(), h['truncated'].data_ptr(),
+          None if obs_h is None else obs_h.data_ptr(), b.obs_stride, stream.cuda_stream), "qcd_step_host")
+    stream.synchronize()
+    return (None if obs_h is None else obs_h.numpy(), h['reward'].numpy(),
+            h['terminated'].numpy().view(np.bool_), h['truncated'].numpy().view(np.bool_))
+
+  def host_bytes_per_step(self, action_dtype=np.float32, copy_obs: bool = True):
+    """(h2d, d2h) bytes `step_host` moves per call."""
+    N, b = self.num_envs, self.batch
+    h2d = N * 4 * np.dtype(action_dtype).itemsize
+    d2h = N * (8 + 1 + 1) + (N * 2 * b.S * 4 if (copy_obs and b.obs is not None) else 0)
+    return h2d, d2h
+
+  # ------------------------------------------------------------------------------------------
+  def accumulate_stats(self) -> None:
+    """Fold the last step's finished episodes into the running statistics vector (device)."""
+    self.batch.reduce_stats()
+
+  def episode_stats(self, reset: bool = False) -> dict:
+    """Running sums as a dict (synchronises)."""
+    vec = self.batch.stats.cpu().numpy().copy()
+    if reset:
+      self.batch.stats.zero_()
+    return dict(zip(_lib.STAT_NAMES, vec.tolist()))
+
+  def close(self):
+    pass

@@ -1,0 +1,148 @@
+"""Parity of the CUDA path (through the C-ABI, via qcd_b200.batch.EnvBatch) with the oracle.
+
+Bar (north_star): depth / operations / used_wires / terminated / truncated / status bit-exact;
+state, metric, cost, reward within 1e-12 (complex128); float32 observations equal to float32(oracle)
+up to the 1e-12 state difference (<= 1 ulp)."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.batch_oracle import OracleBatch
+from oracle.qcd_oracle import make_target
+from tests.helpers import CONFIGS, uniform_box_tape
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+OBS_TOL = 1.2e-7      # one float32 ulp at |x| <= 1
+
+
+def _cmp(gpu, ora, final_mask=None, what=""):
+  g = lambda t: t.cpu().numpy()
+  for name in ('depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status', 'meta',
+               'ep_length', 'episode_length'):
+    a, b = getattr(gpu, name), getattr(ora, name)
+    if a is None: continue
+    if name == 'episode_length' and final_mask is not None:
+      np.testing.assert_array_equal(g(a)[final_mask], b[final_mask], err_msg=f"{what}:{name}")
+    else:
+      np.testing.assert_array_equal(g(a), b, err_msg=f"{what}:{name}")
+  for name in ('reward', 'metric', 'cost', 'last', 'ep_return'):
+    a, b = getattr(gpu, name), getattr(ora, name)
+    if a is None: continue
+    np.testing.assert_allclose(g(a), b, atol=TOL, rtol=0, err_msg=f"{what}:{name}")
+  np.testing.assert_allclose(g(gpu.state), ora.state, atol=TOL, rtol=0, err_msg=f"{what}:state")
+  if gpu.obs is not None:
+    np.testing.assert_allclose(g(gpu.obs), ora.obs, atol=OBS_TOL, rtol=0, err_msg=f"{what}:obs")
+  if gpu.final_obs is not None and final_mask is not None and final_mask.any():
+    np.testing.assert_allclose(g(gpu.final_obs)[final_mask], ora.final_obs[final_mask], atol=OBS_TOL, rtol=0)
+    np.testing.assert_allclose(g(gpu.episode_return)[final_mask], ora.episode_return[final_mask], atol=TOL, rtol=0)
+
+
+def _pair(N, eta, delta, objective, target, **kw):
+  from qcd_b200.batch import EnvBatch
+  return EnvBatch(N, eta, delta, objective, target, **kw), OracleBatch(N, eta, delta, objective, target, **kw)
+
+
+@pytest.mark.parametrize("objective,eta,delta", CONFIGS + [('SP-random', 9, 24), ('SP-random', 12, 36), ('UC-random', 6, 24), ('UC-random', 5, 20)])
+@pytest.mark.parametrize("sparse,punish,act_dtype", [(True, True, np.float32), (False, True, np.float64), (False, False, np.float32)])
+def test_step_matches_oracle(cuda_device, objective, eta, delta, sparse, punish, act_dtype):
+  rng = np.random.default_rng(zlib.crc32(repr((objective, eta, sparse, punish)).encode()))
+  big = (4 ** eta if 'UC' in objective else 2 ** eta) >= 512
+  N, T = (37, 24) if big else (301, 60)
+  target = make_target(objective, eta, seed=5)
+  gpu, ora = _pair(N, eta, delta, objective, target, punish=punish, sparse=sparse, autoreset=True, final_obs=True)
+  _cmp(gpu, ora, what="reset")
+  tape = uniform_box_tape(rng, eta, T, N, dtype=act_dtype, no_terminate=bool(rng.random() < 0.5))
+  dev_tape = torch.as_tensor(tape, device=cuda_device)
+  dones = 0
+  for t in range(T):
+    gpu.step(dev_tape[t]); ora.step(tape[t])
+    fin = (ora.terminated | ora.truncated).astype(bool)
+    dones += int(fin.sum())
+    _cmp(gpu, ora, final_mask=fin, what=f"t={t}")
+  assert dones > 0
+
+
+@pytest.mark.parametrize("objective,eta,delta", [('SP-ghz5', 5, 20), ('UC-toffoli', 3, 30), ('SP-random', 8, 20)])
+def test_no_autoreset_no_obs_and_per_env_targets(cuda_device, objective, eta, delta):
+  rng = np.random.default_rng(9)
+  N, T = 64, 30
+  S = 4 ** eta if 'UC' in objective else 2 ** eta
+  targets = rng.standard_normal((N, S)) + 1j * rng.standard_normal((N, S))
+  targets /= np.linalg.norm(targets, axis=1, keepdims=True)
+  gpu, ora = _pair(N, eta, delta, objective, targets, autoreset=False, obs_mode='state')
+  assert gpu.per_env_target
+  tape = uniform_box_tape(rng, eta, T, N, no_terminate=True)
+  for t in range(T):
+    gpu.step(torch.as_tensor(tape[t], device=cuda_device)); ora.step(tape[t])
+    _cmp(gpu, ora, what=f"t={t}")
+  assert ora.truncated.all()          # stepped past the depth limit without a reset: still identical
+  gpu2, ora2 = _pair(N, eta, delta, objective, targets[0], obs_mode='none')
+  for t in range(5):
+    gpu2.step(torch.as_tensor(tape[t], device=cuda_device)); ora2.step(tape[t])
+    _cmp(gpu2, ora2, what=f"noobs t={t}")
+
+
+def test_invalid_actions_status_and_masked_reset(cuda_device):
+  target = make_target('SP-ghz3', 3)
+  gpu, ora = _pair(5, 3, 15, 'SP-ghz3', target)
+  ok = np.array([[1, 0, 0, 1.0]] * 5)
+  bad = np.array([[0, 3, 0, 0], [0, 0, -0.5, 0], [3, 0, 0, 0], [float('nan'), 0, 0, 0], [1, 1, 0, 0.3]])
+  for a in (ok, bad, ok):
+    gpu.step(torch.as_tensor(a, device=cuda_device)); ora.step(a)
+    _cmp(gpu, ora)
+  assert gpu.status.cpu().tolist() == [0, 0, 0, 0, 0]
+  mask = np.array([1, 0, 1, 0, 0], np.uint8)
+  gpu.reset(torch.as_tensor(mask)); ora.reset(mask)
+  _cmp(gpu, ora, what="masked reset")
+
+
+@pytest.mark.parametrize("objective,eta,delta", CONFIGS + [('SP-random', 12, 36), ('UC-random', 6, 24), ('SP-random', 11, 30)])
+@pytest.mark.parametrize("sparse", [True, False])
+def test_replay_equals_repeated_steps(cuda_device, objective, eta, delta, sparse):
+  """qcd_replay(T) must leave every buffer exactly as T qcd_step launches do (same arithmetic,
+  state kept in shared memory), and its per-step records must equal the per-step outputs."""
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(zlib.crc32(repr((objective, eta, sparse, 'replay')).encode()))
+  big = (4 ** eta if 'UC' in objective else 2 ** eta) >= 512
+  N, T = (19, 20) if big else (157, 48)
+  target = make_target(objective, eta, seed=3)
+  kw = dict(punish=True, sparse=sparse, autoreset=True)
+  a = EnvBatch(N, eta, delta, objective, target, **kw)
+  b = EnvBatch(N, eta, delta, objective, target, **kw)
+  tape = torch.as_tensor(uniform_box_tape(rng, eta, T, N), device=cuda_device)
+  rec = {k: torch.zeros((T, N), dtype=dt, device=cuda_device) for k, dt in
+         [('reward', torch.float64), ('metric', torch.float64), ('cost', torch.float64), ('depth', torch.int32),
+          ('terminated', torch.uint8), ('truncated', torch.uint8), ('status', torch.int8)]}
+  b.replay(tape, rec)
+  for t in range(T):
+    a.step(tape[t])
+    for k in rec:
+      assert torch.equal(rec[k][t], getattr(a, k)), f"{k} t={t}"
+  for name in ('state', 'meta', 'last', 'ep_return', 'ep_length', 'obs', 'reward', 'metric', 'cost', 'depth',
+               'operations', 'used_wires', 'terminated', 'truncated', 'status', 'episode_return', 'episode_length'):
+    assert torch.equal(getattr(a, name), getattr(b, name)), name
+  # sparse replay without a metric record only evaluates the metric where it is needed
+  if sparse:
+    c = EnvBatch(N, eta, delta, objective, target, **kw)
+    rec2 = {'reward': torch.zeros((T, N), dtype=torch.float64, device=cuda_device)}
+    c.replay(tape, rec2)
+    assert torch.equal(rec2['reward'], rec['reward']) and torch.equal(c.state, a.state)
+
+
+def test_stats_reduction(cuda_device):
+  rng = np.random.default_rng(2)
+  N, T, eta, delta = 1000, 40, 3, 15
+  target = make_target('SP-ghz3', eta)
+  gpu, ora = _pair(N, eta, delta, 'SP-ghz3', target)
+  tape = uniform_box_tape(rng, eta, T, N)
+  want = np.zeros(12)
+  for t in range(T):
+    gpu.step(torch.as_tensor(tape[t], device=cuda_device)); gpu.reduce_stats(); ora.step(tape[t])
+    fin = (ora.terminated | ora.truncated).astype(bool)
+    want += [fin.sum(), ora.episode_return[fin].sum(), ora.episode_length[fin].sum(), ora.depth[fin].sum(),
+             ora.operations[fin].sum(), ora.used_wires[fin].sum(), ora.metric[fin].sum(), ora.cost[fin].sum(),
+             (fin & ~ora.truncated.astype(bool)).sum(), ora.truncated.sum(), N, 0]
+  np.testing.assert_allclose(gpu.stats.cpu().numpy(), want, rtol=1e-12)
