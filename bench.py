@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py — batched env-steps/s of the CircuitDesigner hot path on B200, next to the CPU path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sp-ghz5]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE launch of the fused step kernel over one batch of `envs` environments (one
+`env.step()` of every env: decode, gate, depth, metric, cost, reward, float32 observation,
+auto-reset, episode statistics).  Default workload = BASELINE.json configs[1]: SP-ghz5, 65 536 envs
+per GPU, max_depth 20, actions drawn like the reference's own sampler (Box.sample(),
+plot/metrics.py:174).  Weak scaling: every rank owns `envs` envs; the only collective is one
+all-reduce of the 96-byte episode-statistics vector at the end of the timed region.
+
+L2 policy: the batch (57 MB at the default) fits the 126 MB L2, so the bench holds R independent
+replicas of the batch (total footprint >= 3x L2) and steps them round-robin: every launch finds its
+inputs in HBM, not in L2 ("inputs larger than L2").
+
+One JSON line on stdout (rank 0).  `value` = device-timed whole-job throughput with inputs resident
+in HBM; `e2e` = the same metric through CircuitDesignerVectorEnv.step_host (pinned host actions in,
+host reward/terminated/truncated/observations out, every step); `roofline` = algorithmic bytes per
+launch / average launch time vs the measured HBM copy peak; `cpu_baseline` = the numpy oracle port of
+the reference's per-step algorithm timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (objective, eta, delta, envs per GPU, mode)
+    'sp-bell': ('SP-bell', 2, 12, 65536, 'step'),
+    'sp-ghz5': ('SP-ghz5', 5, 20, 65536, 'step'),                 # BASELINE.json configs[1] (headline)
+    'uc-toffoli': ('UC-toffoli', 3, 30, 65536, 'step'),           # configs[2]
+    'sp-random12': ('SP-random', 12, 36, 16384, 'step'),          # configs[3] shape (N scaled to --envs)
+    'uc-random6': ('UC-random', 6, 24, 16384, 'step'),            # configs[4] shape, step kernel
+    'uc-random6-replay': ('UC-random', 6, 24, 4096, 'replay'),    # configs[4]: replay kernel, T=64
+}
+METRIC = "batched env-steps/sec"
+UNIT = "env-steps/s"
+L2_BYTES = 126e6
+TAPE_LEN = 16
+REPLAY_T = 64
+
+
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    try:
+      return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+      pass
+  return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+  """NVML sampler thread: SM clock + throttle reasons DURING the timed region."""
+
+  def __init__(self, index: int, period_s: float = 0.01):
+    self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+    self._stop = threading.Event()
+    self._thread = None
+    self.period = period_s
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+      self.ok = True
+    except Exception as exc:            # no NVML: report that instead of inventing numbers
+      self.err = repr(exc)
+
+  def _names(self, mask: int):
+    nv = self.nv
+    table = {'sw_power_cap': 'nvmlClocksThrottleReasonSwPowerCap', 'hw_slowdown': 'nvmlClocksThrottleReasonHwSlowdown',
+             'hw_thermal_slowdown': 'nvmlClocksThrottleReasonHwThermalSlowdown',
+             'sw_thermal_slowdown': 'nvmlClocksThrottleReasonSwThermalSlowdown',
+             'hw_power_brake': 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown',
+             'sync_boost': 'nvmlClocksThrottleReasonSyncBoost',
+             'app_clocks': 'nvmlClocksThrottleReasonApplicationsClocksSetting'}
+    return {k for k, attr in table.items() if mask & getattr(nv, attr, 0)}
+
+  def sample(self):
+    if not self.ok:
+      return
+    try:
+      self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+      self.reasons |= self._names(int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+    except Exception:
+      pass
+
+  def _run(self):
+    while not self._stop.is_set():
+      self.sample()
+      self._stop.wait(self.period)
+
+  def start(self):
+    if self.ok:
+      self._thread = threading.Thread(target=self._run, daemon=True)
+      self._thread.start()
+
+  def stop(self):
+    self.sample()
+    self._stop.set()
+    if self._thread is not None:
+      self._thread.join()
+
+  def summary(self):
+    if not self.ok or not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+    return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_tape(n_qubits: int, T: int, N: int, seed: int):
+  """[T,N,4] float32 actions ~ Box.sample() of env.py:46-49 (uniform in the float32 bounds)."""
+  m = 1e-5
+  low = np.array([0, 0, 0, -np.pi]).astype(np.float32)
+  high = np.array([3 - m, n_qubits - m, n_qubits - m, np.pi]).astype(np.float32)
+  rng = np.random.default_rng(seed)
+  return rng.uniform(low=low, high=high, size=(T, N, 4)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_steps_per_s(objective, eta, delta, tape, budget_s: float, max_envs: int = 64):
+  """Time the numpy oracle port (reference per-step algorithm: re-simulate the circuit for the
+  observation and again for the reward, walk it for depth) on ONE core for ~budget_s seconds."""
+  from oracle.qcd_oracle import OracleCircuitDesigner, make_target
+  target = make_target(objective, eta, seed=42)
+  T, N = tape.shape[0], min(tape.shape[1], max_envs)
+  envs = [OracleCircuitDesigner(eta, delta, objective, target=target) for _ in range(N)]
+  for e in envs:
+    e.reset()
+  steps, t0, t = 0, time.perf_counter(), 0
+  while True:
+    for i, e in enumerate(envs):
+      _, _, term, trunc, _ = e.step(tape[t % T, i])
+      if term or trunc:
+        e.reset()
+    steps += N
+    t += 1
+    if time.perf_counter() - t0 >= budget_s:
+      break
+  dt = time.perf_counter() - t0
+  return steps / dt, steps, dt
+
+
+def _ref_worker(args):
+  objective, eta, delta, tape, n_steps = args
+  from oracle.qcd_oracle import OracleCircuitDesigner, make_target
+  target = make_target(objective, eta, seed=42)
+  N = tape.shape[1]
+  envs = [OracleCircuitDesigner(eta, delta, objective, target=target) for _ in range(N)]
+  for e in envs:
+    e.reset()
+  # state persists in the worker between calls through this closure-free global
+  global _REF_ENVS
+  _REF_ENVS = envs
+  return N
+
+
+def _ref_step(args):
+  tape_row, = args
+  for i, e in enumerate(_REF_ENVS):
+    _, _, term, trunc, _ = e.step(tape_row[i])
+    if term or trunc:
+      e.reset()
+  return len(_REF_ENVS)
+
+
+def run_reference(args):
+  """--impl reference: the reference's CPU implementation of the path (oracle port; qiskit itself is
+  not installable here) on all host cores.  One step = one env.step() of a bounded sample of the
+  workload's envs, spread over one worker process per core."""
+  import multiprocessing as mp
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return 0
+  objective, eta, delta, envs, mode = WORKLOADS[args.workload]
+  cores = os.cpu_count() or 1
+  per_worker = args.ref_envs_per_core
+  tape = make_tape(eta, TAPE_LEN, per_worker * cores, seed=1234)
+  ctx = mp.get_context("fork")
+  # one single-process pool per core so that each worker keeps its own envs between steps
+  pools = [ctx.Pool(1) for _ in range(cores)]
+  try:
+    for w, p in enumerate(pools):
+      p.apply(_ref_worker, ((objective, eta, delta, tape[:, w * per_worker:(w + 1) * per_worker], 0),))
+
+    def one_step(t):
+      res = [p.apply_async(_ref_step, ((tape[t % TAPE_LEN, w * per_worker:(w + 1) * per_worker],),))
+             for w, p in enumerate(pools)]
+      return sum(r.get() for r in res)
+
+    for t in range(args.warmup):
+      one_step(t)
+    t0 = time.perf_counter()
+    total = 0
+    for t in range(args.steps):
+      total += one_step(args.warmup + t)
+    dt = time.perf_counter() - t0
+  finally:
+    for p in pools:
+      p.terminate()
+  value = total / dt
+  sample = (f"{per_worker * cores} of {envs} envs per step ({per_worker} per core), same Box.sample() "
+            f"action distribution, numpy restatement of env.py on qiskit-1.0.2 semantics")
+  line = {
+      "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+      "data": "synthetic",
+      "config": {"workload": f"{objective} eta={eta} max_depth={delta} envs={envs} (reference arm: "
+                             f"{per_worker * cores}-env sample per step)", "actions": "uniform-box"},
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+      "note": "qiskit==1.0.2/gymnasium==0.29 are not installable in this image; the timed code is "
+              "oracle/qcd_oracle.py, which follows the reference's per-step algorithm",
+  }
+  print(json.dumps(line), flush=True)
+  return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+  import torch
+  import torch.distributed as dist
+  from qcd_b200.batch import EnvBatch
+  from qcd_b200.sharding import all_reduce_stats, summarize
+  from qcd_b200.targets import make_target
+  from qcd_b200.vector_env import CircuitDesignerVectorEnv
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device: qcd_b200 has no CPU fallback")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  if world != args.gpus and rank == 0:
+    print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+  objective, eta, delta, envs, mode = WORKLOADS[args.workload]
+  N = args.envs or envs
+  target = make_target(objective, eta, seed=42)
+  K, W = args.steps, args.warmup
+  obs_mode = args.obs
+
+  # ---- R replicas of the batch so that consecutive launches never find their data in L2
+  probe = EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs, device=dev)
+  S = probe.S
+  bytes_step_env = probe.algorithmic_bytes_per_step()
+  footprint = N * (16 * S + (8 * S if obs_mode != 'none' else 0) + 96)
+  R = max(2, int(np.ceil(3 * L2_BYTES / footprint))) if not args.no_rotate else 1
+  free, _ = torch.cuda.mem_get_info(dev)
+  per_replica = N * (16 * S + (4 * probe.obs_stride if obs_mode != 'none' else 0) * (2 if args.final_obs else 1) + 200)
+  R = max(1, min(R, int(0.8 * free // per_replica)))
+  batches = [probe] + [EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
+                                device=dev) for _ in range(R - 1)]
+  tape_np = make_tape(eta, TAPE_LEN if mode == 'step' else REPLAY_T * 2, N, seed=1234 + rank)
+  tape = torch.as_tensor(tape_np, device=dev)
+
+  if mode == 'step':
+    steps_per_launch = 1
+
+    def launch(i):
+      batches[i % R].step(tape[i % TAPE_LEN])
+  else:
+    steps_per_launch = REPLAY_T
+
+    def launch(i):
+      batches[i % R].replay(tape[(i % 2) * REPLAY_T:(i % 2 + 1) * REPLAY_T])
+
+  # ---- CUDA graph of G consecutive launches (launch-bound otherwise: ~20 us kernels)
+  G = int(np.lcm(R, TAPE_LEN)) if mode == 'step' else R * 2
+  G = min(G, max(1, K))
+  stream = torch.cuda.Stream(dev)
+  graph = None
+  with torch.cuda.stream(stream):
+    for i in range(max(W, 3)):
+      launch(i)
+    stream.synchronize()
+    if not args.no_graph:
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph, stream=stream):
+        for i in range(G):
+          launch(i)
+      graph.replay()
+      stream.synchronize()
+
+  def run_steps(k):
+    done = 0
+    if graph is not None:
+      while done + G <= k:
+        graph.replay()
+        done += G
+    while done < k:
+      launch(done)
+      done += 1
+
+  clocks = ClockSampler(local)
+  with torch.cuda.stream(stream):
+    run_steps(W)
+    stream.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.start()
+    ev0.record(stream)
+    run_steps(K)
+    # the one collective of the path: episode statistics of all ranks (96 B) over NCCL/NVLink
+    stats = torch.stack([b.stats for b in batches]).sum(0)
+    all_reduce_stats(stats)
+    ev1.record(stream)
+    stream.synchronize()
+    clocks.stop()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+  elapsed_ms = ev0.elapsed_time(ev1)
+  t_all = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+  elapsed_ms = float(t_all.item())
+  env_steps = N * K * steps_per_launch * world
+  value = env_steps / (elapsed_ms * 1e-3)
+
+  # ---- end to end through the public API with HOST buffers (step workloads only)
+  e2e = None
+  if mode == 'step':
+    venv = CircuitDesignerVectorEnv(N, eta, delta, objective, target=target, device=dev, obs_mode=obs_mode)
+    venv.reset()
+    Ke = max(3, min(K, args.e2e_steps))
+    with torch.cuda.stream(stream):
+      for i in range(3):
+        venv.step_host(tape_np[i % TAPE_LEN], copy_obs=not args.e2e_no_obs)
+      if world > 1:
+        dist.barrier()
+      torch.cuda.synchronize(dev)
+      t0 = time.perf_counter()
+      for i in range(Ke):
+        venv.step_host(tape_np[i % TAPE_LEN], copy_obs=not args.e2e_no_obs)   # syncs every step
+      torch.cuda.synchronize(dev)
+      dt = time.perf_counter() - t0
+    t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    h2d, d2h = venv.host_bytes_per_step(np.float32, copy_obs=not args.e2e_no_obs)
+    e2e = {"value": N * Ke * world / float(t_e.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "steps": Ke, "ms_per_step": float(t_e.item()) / Ke * 1e3,
+           "api": "CircuitDesignerVectorEnv.step_host -> qcd_step_host (pinned host buffers, sync per step)",
+           "obs_copied": not args.e2e_no_obs}
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return 0
+
+  # ---- roofline of the dominant kernel (the only kernel in the timed region)
+  peak, peak_src = load_peaks()
+  launch_ms = elapsed_ms / K
+  if mode == 'step':
+    alg_bytes = bytes_step_env * N
+  else:   # replay: state in + out once per launch, actions per step, scalars once
+    alg_bytes = N * (32 * S + (8 * S if obs_mode != 'none' else 0) + 96 + 16 * REPLAY_T)
+  achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+  traffic = None
+  tpath = os.path.join(ROOT, "profiles", "traffic.json")
+  if os.path.exists(tpath):
+    try:
+      traffic = json.load(open(tpath)).get(args.workload)
+    except Exception:
+      traffic = None
+  roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+              "traffic": traffic, "peak_source": peak_src, "kernel": "qcd::qcd_kernel<%d,%s,%s>" % (
+                  int(np.log2(S)), "UC" if 'UC' in objective else "SP", "step" if mode == 'step' else "replay"),
+              "algorithmic_bytes_per_env_step": bytes_step_env, "launch_us": launch_ms * 1e3}
+
+  # ---- CPU baseline beside it (rank 0, one core, bounded sample)
+  cpu = None
+  if not args.no_cpu:
+    v, n_steps, dt = cpu_port_steps_per_s(objective, eta, delta, tape_np, args.cpu_seconds)
+    cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"first {min(N, 64)} envs of the batch, {n_steps} env-steps in {dt:.1f} s, same action tape; "
+                     f"numpy restatement of env.py (re-simulates the circuit twice per step like the reference); "
+                     f"host has {os.cpu_count()} cores"}
+
+  line = {
+      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+      "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "complex128", "data": "synthetic",
+      "config": {"workload": f"{objective} eta={eta} max_depth={delta} envs_per_gpu={N}", "mode": mode,
+                 "envs_total": N * world, "actions": "uniform-box float32 (Box.sample distribution), tape of "
+                 f"{TAPE_LEN} steps reused", "punish": True, "sparse": True, "autoreset": True,
+                 "observations": obs_mode, "final_obs": bool(args.final_obs), "fused_stats": True,
+                 "l2": f"{R} batch replicas stepped round-robin, footprint {R * footprint / 1e6:.0f} MB > L2 "
+                       f"126 MB" if R > 1 else "single batch (no rotation)",
+                 "cuda_graph": graph is not None, "graph_len": G if graph is not None else 0,
+                 "steps_per_launch": steps_per_launch, "parallelism": f"env-sharded x{world}, stats all-reduce only"},
+      "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu,
+      "episode_stats": summarize(stats),
+  }
+  print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+  return 0
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=4000)
+  ap.add_argument("--warmup", type=int, default=200)
+  ap.add_argument("--impl", default="native", choices=["native", "reference"])
+  ap.add_argument("--workload", default="sp-ghz5", choices=sorted(WORKLOADS))
+  ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+  ap.add_argument("--obs", default="full", choices=["full", "state", "none"])
+  ap.add_argument("--final-obs", action="store_true", help="also write terminal observations of finished envs")
+  ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--no-rotate", action="store_true", help="single batch replica (L2-resident at small sizes)")
+  ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--cpu-seconds", type=float, default=10.0)
+  ap.add_argument("--e2e-steps", type=int, default=200)
+  ap.add_argument("--e2e-no-obs", action="store_true", help="e2e without the observation D2H copy")
+  ap.add_argument("--ref-envs-per-core", type=int, default=64)
+  args = ap.parse_args()
+  if args.warmup < 3:
+    args.warmup = 3
+  if args.impl == "reference":
+    return run_reference(args)
+  return run_native(args)
+
+
+if __name__ == "__main__":
+  sys.exit(main())

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 1
+#define QCD_ABI_VERSION 2
 
 #define QCD_MAX_QUBITS_SP 12   /* S = 4096 complex128 = 64 KiB per env */
 #define QCD_MAX_QUBITS_UC 6    /* 64x64 unitary      = 64 KiB per env */
@@ -99,6 +99,8 @@ typedef struct qcd_batch {
   int8_t*  status;          /* [N] QCD_ST_*                                               */
   double*  episode_return;  /* [N] or NULL: Monitor 'r' latched when the episode finishes */
   int32_t* episode_length;  /* [N] or NULL: Monitor 'l' latched when the episode finishes */
+  double*  stats;           /* [QCD_STATS_LEN] or NULL: running episode statistics, accumulated (+=)
+                               by qcd_step / qcd_replay themselves (fused; no extra launch)        */
 } qcd_batch_t;
 
 /* Per-step outputs of a replay over T steps; every pointer may be NULL (not recorded).
@@ -141,7 +143,8 @@ int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int3
                const qcd_tape_out_t* out, void* stream);
 
 /* Adds this step's finished-episode statistics (see QCD_STAT_*) to stats[QCD_STATS_LEN] (float64,
- * device).  Reads only the per-step outputs of `b`. */
+ * device).  Reads only the per-step outputs of `b`.  Stand-alone variant of the accumulation that
+ * qcd_step / qcd_replay fuse when b->stats != NULL (do not use both on the same vector). */
 int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream);
 
 /* Host-buffer convenience used by the end-to-end path: copy `actions_host` (pinned) to

@@ -34,7 +34,7 @@ class _Batch(C.Structure):
       ("reward", C.c_void_p), ("metric", C.c_void_p), ("cost", C.c_void_p),
       ("depth", C.c_void_p), ("operations", C.c_void_p), ("used_wires", C.c_void_p),
       ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("status", C.c_void_p),
-      ("episode_return", C.c_void_p), ("episode_length", C.c_void_p),
+      ("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stats", C.c_void_p),
   ]
 
 
@@ -70,6 +70,7 @@ class OracleBatch:
     self.reward = np.zeros(N, np.float64); self.metric = np.zeros(N, np.float64); self.cost = np.zeros(N, np.float64)
     self.depth = np.zeros(N, np.int32); self.operations = np.zeros(N, np.int32); self.used_wires = np.zeros(N, np.int32)
     self.terminated = np.zeros(N, np.uint8); self.truncated = np.zeros(N, np.uint8); self.status = np.zeros(N, np.int8)
+    self.stats = np.zeros(12, np.float64)
     self.obs = self.final_obs = None
     self.obs_stride = 2 * S
     if obs_mode != 'none':
@@ -88,7 +89,7 @@ class OracleBatch:
                     p(self.ep_return), p(self.ep_length), p(self.obs), p(self.final_obs),
                     p(self.reward), p(self.metric), p(self.cost), p(self.depth), p(self.operations),
                     p(self.used_wires), p(self.terminated), p(self.truncated), p(self.status),
-                    p(self.episode_return), p(self.episode_length))
+                    p(self.episode_return), p(self.episode_length), p(self.stats))
     self.reset()
 
   def reset(self, mask=None):

@@ -31,6 +31,7 @@ typedef struct {
   int32_t* depth; int32_t* operations; int32_t* used_wires;
   uint8_t* terminated; uint8_t* truncated; int8_t* status;
   double* episode_return; int32_t* episode_length;
+  double* stats;   /* [12] running episode statistics (monitor.py:37-48, algorithm.py:112-114) or NULL */
 } batch_t;
 
 static void write_obs(float* row, const double* st, long S) {   /* env.py:10 flat(): [Re | Im] float32 */
@@ -172,6 +173,19 @@ int oracle_step(const batch_t* b, const double* actions) {
     b->terminated[e] = (uint8_t)term; b->truncated[e] = (uint8_t)trunc; b->status[e] = (int8_t)status;
 
     if (done && b->episode_return) { b->episode_return[e] = b->ep_return[e]; b->episode_length[e] = b->ep_length[e]; }
+    if (b->stats) {     /* same fields, same order as QCD_STAT_* in include/qcd_b200.h */
+      double* s = b->stats;
+      if (status != 0) s[11] += 1;
+      else {
+        s[10] += 1;
+        if (done) {
+          s[0] += 1;
+          if (b->ep_return) { s[1] += b->ep_return[e]; s[2] += b->ep_length[e]; }
+          s[3] += depth; s[4] += ops; s[5] += nused; s[6] += m; s[7] += cc;
+          if (trunc) s[9] += 1; else s[8] += 1;
+        }
+      }
+    }
     if (done && (b->flags & F_AUTORESET)) {
       if (b->final_obs) write_obs(b->final_obs + e * b->obs_stride, st, S);
       reset_state(st, S, uc, eta);

@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 STATS_LEN = 12
 STAT_NAMES = ("episodes", "sum_r", "sum_l", "sum_d", "sum_o", "sum_q", "sum_m", "sum_c",
               "n_done", "n_depth", "steps", "bad_actions")
@@ -34,7 +34,7 @@ class QcdBatch(C.Structure):
       ("reward", C.c_void_p), ("metric", C.c_void_p), ("cost", C.c_void_p),
       ("depth", C.c_void_p), ("operations", C.c_void_p), ("used_wires", C.c_void_p),
       ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("status", C.c_void_p),
-      ("episode_return", C.c_void_p), ("episode_length", C.c_void_p),
+      ("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stats", C.c_void_p),
   ]
 
 

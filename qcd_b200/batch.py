@@ -38,7 +38,7 @@ class EnvBatch:
 
   def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str, target,
                punish: bool = True, sparse: bool = True, autoreset: bool = True, obs_mode: str = 'full',
-               final_obs: bool = False, track_episodes: bool = True, device=None):
+               final_obs: bool = False, track_episodes: bool = True, fused_stats: bool = True, device=None):
     if not torch.cuda.is_available():
       raise RuntimeError("qcd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     self.lib = _lib.load_library()
@@ -112,7 +112,9 @@ class EnvBatch:
         reward=_ptr(self.reward), metric=_ptr(self.metric), cost=_ptr(self.cost),
         depth=_ptr(self.depth), operations=_ptr(self.operations), used_wires=_ptr(self.used_wires),
         terminated=_ptr(self.terminated), truncated=_ptr(self.truncated), status=_ptr(self.status),
-        episode_return=_ptr(self.episode_return), episode_length=_ptr(self.episode_length))
+        episode_return=_ptr(self.episode_return), episode_length=_ptr(self.episode_length),
+        stats=_ptr(self.stats) if fused_stats else None)
+    self.fused_stats = bool(fused_stats)
     self._cref = C.byref(self.c)
     self.reset()
 
@@ -170,7 +172,10 @@ class EnvBatch:
                                 self._stream()), "qcd_replay")
 
   def reduce_stats(self) -> None:
-    """Add the finished-episode statistics of the last step to `self.stats`."""
+    """Add the finished-episode statistics of the last step to `self.stats` (stand-alone launch;
+    a no-op when the step kernel already accumulates them, `fused_stats=True`)."""
+    if self.fused_stats:
+      return
     with torch.cuda.device(self.device):
       check(self.lib.qcd_reduce_stats(self._cref, self.stats.data_ptr(), self._stream()), "qcd_reduce_stats")
 

@@ -357,6 +357,8 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
     }
 
     // ================= phase 3: per-env finalize + scalar outputs
+    int st_fin = 0, st_ok = 0, st_bad = 0, st_trunc = 0, st_l = 0, st_d = 0, st_o = 0, st_q = 0;
+    double st_r = 0.0, st_m = 0.0, st_c = 0.0;
     if (ctl) {
       const double2 r = s_red[tid];
       const bool have_metric = s_rec[tid].flags & RF_METRIC;
@@ -374,11 +376,48 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
         b.depth[cenv] = e.depth; b.operations[cenv] = e.ops; b.used_wires[cenv] = e.used_cnt;
         b.terminated[cenv] = e.term; b.truncated[cenv] = e.trunc; b.status[cenv] = (int8_t)e.status;
       }
+      st_ok = e.status == QCD_ST_OK; st_bad = !st_ok;
       if (done) {
+        st_fin = 1; st_trunc = e.trunc; st_l = e.ep_len; st_d = e.depth; st_o = e.ops; st_q = e.used_cnt;
+        st_r = e.ep_ret; st_m = o.metric; st_c = o.cost;
         if (b.episode_return) { b.episode_return[cenv] = e.ep_ret; b.episode_length[cenv] = e.ep_len; }
         if (autoreset) {                          // env.py:117-121 fused
           e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
         }
+      }
+    }
+    // Fused K3: Monitor episode fields + termination histogram summed over the warp, then one
+    // atomicAdd per non-zero field per warp of control threads (warp-uniform branch).
+    if (b.stats != nullptr && (tid >> 5) <= ((E - 1) >> 5)) {
+      constexpr unsigned FULL = 0xffffffffu;
+      const int n_fin = __reduce_add_sync(FULL, st_fin);
+      const int n_ok = __reduce_add_sync(FULL, st_ok);
+      const int n_bad = __reduce_add_sync(FULL, st_bad);
+      if (n_fin) {
+        const int n_trunc = __reduce_add_sync(FULL, st_trunc);
+        const int s_l = __reduce_add_sync(FULL, st_l), s_d = __reduce_add_sync(FULL, st_d);
+        const int s_o = __reduce_add_sync(FULL, st_o), s_q = __reduce_add_sync(FULL, st_q);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          st_r += __shfl_xor_sync(FULL, st_r, off);
+          st_m += __shfl_xor_sync(FULL, st_m, off);
+          st_c += __shfl_xor_sync(FULL, st_c, off);
+        }
+        if ((tid & 31) == 0) {
+          atomicAdd(b.stats + QCD_STAT_EPISODES, (double)n_fin);
+          if (b.ep_return) { atomicAdd(b.stats + QCD_STAT_SUM_R, st_r); atomicAdd(b.stats + QCD_STAT_SUM_L, (double)s_l); }
+          atomicAdd(b.stats + QCD_STAT_SUM_D, (double)s_d);
+          atomicAdd(b.stats + QCD_STAT_SUM_O, (double)s_o);
+          atomicAdd(b.stats + QCD_STAT_SUM_Q, (double)s_q);
+          atomicAdd(b.stats + QCD_STAT_SUM_M, st_m);
+          atomicAdd(b.stats + QCD_STAT_SUM_C, st_c);
+          if (n_fin - n_trunc) atomicAdd(b.stats + QCD_STAT_N_DONE, (double)(n_fin - n_trunc));
+          if (n_trunc) atomicAdd(b.stats + QCD_STAT_N_DEPTH, (double)n_trunc);
+        }
+      }
+      if ((tid & 31) == 0) {
+        if (n_ok) atomicAdd(b.stats + QCD_STAT_STEPS, (double)n_ok);
+        if (n_bad) atomicAdd(b.stats + QCD_STAT_BAD_ACTIONS, (double)n_bad);
       }
     }
     // No barrier needed here: s_rec[tid] / s_red[tid] are re-written in phase 1 / phase 2 of step

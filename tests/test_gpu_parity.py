@@ -54,7 +54,7 @@ def test_step_matches_oracle(cuda_device, objective, eta, delta, sparse, punish,
   target = make_target(objective, eta, seed=5)
   gpu, ora = _pair(N, eta, delta, objective, target, punish=punish, sparse=sparse, autoreset=True, final_obs=True)
   _cmp(gpu, ora, what="reset")
-  tape = uniform_box_tape(rng, eta, T, N, dtype=act_dtype, no_terminate=bool(rng.random() < 0.5))
+  tape = uniform_box_tape(rng, eta, T, N, dtype=act_dtype, no_terminate=bool(rng.random() < 0.5) and not big)
   dev_tape = torch.as_tensor(tape, device=cuda_device)
   dones = 0
   for t in range(T):
@@ -63,6 +63,8 @@ def test_step_matches_oracle(cuda_device, objective, eta, delta, sparse, punish,
     dones += int(fin.sum())
     _cmp(gpu, ora, final_mask=fin, what=f"t={t}")
   assert dones > 0
+  assert gpu.stats[0].item() == dones == ora.stats[0]
+  np.testing.assert_allclose(gpu.stats.cpu().numpy(), ora.stats, rtol=1e-11, atol=1e-9)   # fused K3
 
 
 @pytest.mark.parametrize("objective,eta,delta", [('SP-ghz5', 5, 20), ('UC-toffoli', 3, 30), ('SP-random', 8, 20)])
@@ -132,11 +134,14 @@ def test_replay_equals_repeated_steps(cuda_device, objective, eta, delta, sparse
     assert torch.equal(rec2['reward'], rec['reward']) and torch.equal(c.state, a.state)
 
 
-def test_stats_reduction(cuda_device):
+@pytest.mark.parametrize("fused", [True, False])
+def test_stats_reduction(cuda_device, fused):
+  from qcd_b200.batch import EnvBatch
   rng = np.random.default_rng(2)
   N, T, eta, delta = 1000, 40, 3, 15
   target = make_target('SP-ghz3', eta)
-  gpu, ora = _pair(N, eta, delta, 'SP-ghz3', target)
+  gpu = EnvBatch(N, eta, delta, 'SP-ghz3', target, fused_stats=fused)
+  ora = OracleBatch(N, eta, delta, 'SP-ghz3', target)
   tape = uniform_box_tape(rng, eta, T, N)
   want = np.zeros(12)
   for t in range(T):
@@ -146,3 +151,4 @@ def test_stats_reduction(cuda_device):
              ora.operations[fin].sum(), ora.used_wires[fin].sum(), ora.metric[fin].sum(), ora.cost[fin].sum(),
              (fin & ~ora.truncated.astype(bool)).sum(), ora.truncated.sum(), N, 0]
   np.testing.assert_allclose(gpu.stats.cpu().numpy(), want, rtol=1e-12)
+  np.testing.assert_allclose(ora.stats, want, rtol=1e-12)
