@@ -262,7 +262,8 @@ def run_native(args):
   obs_mode = args.obs
 
   # ---- R replicas of the batch so that consecutive launches never find their data in L2
-  probe = EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs, device=dev)
+  probe = EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
+                   fused_stats=not args.no_stats, device=dev)
   S = probe.S
   bytes_step_env = probe.algorithmic_bytes_per_step()
   footprint = N * (16 * S + (8 * S if obs_mode != 'none' else 0) + 96)
@@ -271,7 +272,7 @@ def run_native(args):
   per_replica = N * (16 * S + (4 * probe.obs_stride if obs_mode != 'none' else 0) * (2 if args.final_obs else 1) + 200)
   R = max(1, min(R, int(0.8 * free // per_replica)))
   batches = [probe] + [EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
-                                device=dev) for _ in range(R - 1)]
+                                fused_stats=not args.no_stats, device=dev) for _ in range(R - 1)]
   tape_np = make_tape(eta, TAPE_LEN if mode == 'step' else REPLAY_T * 2, N, seed=1234 + rank)
   tape = torch.as_tensor(tape_np, device=dev)
 
@@ -408,7 +409,7 @@ def run_native(args):
       "config": {"workload": f"{objective} eta={eta} max_depth={delta} envs_per_gpu={N}", "mode": mode,
                  "envs_total": N * world, "actions": "uniform-box float32 (Box.sample distribution), tape of "
                  f"{TAPE_LEN} steps reused", "punish": True, "sparse": True, "autoreset": True,
-                 "observations": obs_mode, "final_obs": bool(args.final_obs), "fused_stats": True,
+                 "observations": obs_mode, "final_obs": bool(args.final_obs), "fused_stats": not args.no_stats,
                  "l2": f"{R} batch replicas stepped round-robin, footprint {R * footprint / 1e6:.0f} MB > L2 "
                        f"126 MB" if R > 1 else "single batch (no rotation)",
                  "cuda_graph": graph is not None, "graph_len": G if graph is not None else 0,
@@ -435,6 +436,7 @@ def main():
   ap.add_argument("--no-graph", action="store_true")
   ap.add_argument("--no-rotate", action="store_true", help="single batch replica (L2-resident at small sizes)")
   ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--no-stats", action="store_true", help="do not accumulate episode statistics in the step kernel")
   ap.add_argument("--cpu-seconds", type=float, default=10.0)
   ap.add_argument("--e2e-steps", type=int, default=200)
   ap.add_argument("--e2e-no-obs", action="store_true", help="e2e without the observation D2H copy")

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 2
+#define QCD_ABI_VERSION 3
 
 #define QCD_MAX_QUBITS_SP 12   /* S = 4096 complex128 = 64 KiB per env */
 #define QCD_MAX_QUBITS_UC 6    /* 64x64 unitary      = 64 KiB per env */
@@ -99,8 +99,9 @@ typedef struct qcd_batch {
   int8_t*  status;          /* [N] QCD_ST_*                                               */
   double*  episode_return;  /* [N] or NULL: Monitor 'r' latched when the episode finishes */
   int32_t* episode_length;  /* [N] or NULL: Monitor 'l' latched when the episode finishes */
-  double*  stats;           /* [QCD_STATS_LEN] or NULL: running episode statistics, accumulated (+=)
-                               by qcd_step / qcd_replay themselves (fused; no extra launch)        */
+  double*  stats;           /* [QCD_STATS_COPIES][QCD_STATS_STRIDE] or NULL: running episode statistics,
+                               accumulated (+=) by qcd_step / qcd_replay themselves (fused; no extra
+                               launch).  Field k of the statistics = sum over copies of stats[c][k]    */
 } qcd_batch_t;
 
 /* Per-step outputs of a replay over T steps; every pointer may be NULL (not recorded).
@@ -118,6 +119,8 @@ typedef struct qcd_tape_out {
 /* Episode statistics accumulated by qcd_reduce_stats: the Monitor fields of monitor.py:37-48 and the
  * termination histogram of algorithm/algorithm.py:112-114, summed over finished episodes. */
 #define QCD_STATS_LEN 12
+#define QCD_STATS_COPIES 64      /* replicas of the vector, one 128-byte line each (atomic spreading) */
+#define QCD_STATS_STRIDE 16      /* doubles between replicas                                          */
 enum {
   QCD_STAT_EPISODES = 0, QCD_STAT_SUM_R, QCD_STAT_SUM_L, QCD_STAT_SUM_D, QCD_STAT_SUM_O,
   QCD_STAT_SUM_Q, QCD_STAT_SUM_M, QCD_STAT_SUM_C, QCD_STAT_N_DONE, QCD_STAT_N_DEPTH,
@@ -142,8 +145,8 @@ int qcd_step(const qcd_batch_t* b, const void* actions, int action_dtype, void* 
 int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int32_t n_steps,
                const qcd_tape_out_t* out, void* stream);
 
-/* Adds this step's finished-episode statistics (see QCD_STAT_*) to stats[QCD_STATS_LEN] (float64,
- * device).  Reads only the per-step outputs of `b`.  Stand-alone variant of the accumulation that
+/* Adds this step's finished-episode statistics (see QCD_STAT_*) to stats[QCD_STATS_COPIES]
+ * [QCD_STATS_STRIDE] (float64, device; sum over the copies = the statistics).  Reads only the per-step outputs of `b`.  Stand-alone variant of the accumulation that
  * qcd_step / qcd_replay fuse when b->stats != NULL (do not use both on the same vector). */
 int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream);
 

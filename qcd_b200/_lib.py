@@ -6,8 +6,10 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATS_LEN = 12
+STATS_COPIES = 64
+STATS_STRIDE = 16
 STAT_NAMES = ("episodes", "sum_r", "sum_l", "sum_d", "sum_o", "sum_q", "sum_m", "sum_c",
               "n_done", "n_depth", "steps", "bad_actions")
 

@@ -84,7 +84,7 @@ class EnvBatch:
     self.terminated = torch.zeros(N, dtype=u8, device=dev)
     self.truncated = torch.zeros(N, dtype=u8, device=dev)
     self.status = torch.zeros(N, dtype=torch.int8, device=dev)
-    self.stats = torch.zeros(_lib.STATS_LEN, dtype=f64, device=dev)
+    self._stats_raw = torch.zeros((_lib.STATS_COPIES, _lib.STATS_STRIDE), dtype=f64, device=dev)
 
     self.obs = self.final_obs = None
     self.obs_stride = 2 * S
@@ -113,7 +113,7 @@ class EnvBatch:
         depth=_ptr(self.depth), operations=_ptr(self.operations), used_wires=_ptr(self.used_wires),
         terminated=_ptr(self.terminated), truncated=_ptr(self.truncated), status=_ptr(self.status),
         episode_return=_ptr(self.episode_return), episode_length=_ptr(self.episode_length),
-        stats=_ptr(self.stats) if fused_stats else None)
+        stats=_ptr(self._stats_raw) if fused_stats else None)
     self.fused_stats = bool(fused_stats)
     self._cref = C.byref(self.c)
     self.reset()
@@ -177,7 +177,15 @@ class EnvBatch:
     if self.fused_stats:
       return
     with torch.cuda.device(self.device):
-      check(self.lib.qcd_reduce_stats(self._cref, self.stats.data_ptr(), self._stream()), "qcd_reduce_stats")
+      check(self.lib.qcd_reduce_stats(self._cref, self._stats_raw.data_ptr(), self._stream()), "qcd_reduce_stats")
+
+  @property
+  def stats(self) -> torch.Tensor:
+    """float64 [QCD_STATS_LEN] running episode statistics (sum over the atomic-spreading copies)."""
+    return self._stats_raw.sum(0)[:_lib.STATS_LEN]
+
+  def zero_stats(self) -> None:
+    self._stats_raw.zero_()
 
   # ------------------------------------------------------------------------------------------
   def state_view(self) -> torch.Tensor:

@@ -37,7 +37,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
   """Compile csrc/*.cu -> qcd_b200/libqcd_b200.so.  Returns the library path."""
   if not force and not is_stale():
     return LIB_PATH
-  cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
+  extra = os.environ.get("QCD_NVCC_EXTRA", "").split()      # tuning knobs, e.g. -DQCD_REG_MINB=3
+  cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *SOURCES]
   if verbose:
     cmd.insert(1, "-Xptxas=-v")
   res = subprocess.run(cmd, capture_output=True, text=True)

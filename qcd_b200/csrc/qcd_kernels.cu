@@ -36,6 +36,29 @@
 
 namespace qcd {
 
+#ifndef QCD_REG_STEP_MAX_LOG2S
+#define QCD_REG_STEP_MAX_LOG2S 8     // S <= 256: register-resident step kernel
+#endif
+#ifndef QCD_STEP_IMPL
+#define QCD_STEP_IMPL 2                // small-S step path: 0 pair-streaming, 1 CTA register-resident, 2 warp-autonomous
+#endif
+#ifndef QCD_WARP_STEP_WARPS
+#define QCD_WARP_STEP_WARPS 4
+#endif
+#ifndef QCD_WARP_STEP_MINB
+#define QCD_WARP_STEP_MINB 4
+#endif
+#ifndef QCD_WARP_STEP_TILE
+#define QCD_WARP_STEP_TILE 32          // envs per warp tile (0 = 8 KiB of state per tile, clamped to 8..32)
+#endif
+#ifndef QCD_WARP_STEP_STAGE
+#define QCD_WARP_STEP_STAGE 0         // 1: stage the tile in smem with cp.async.bulk (TMA) when it fits 16 KiB
+                                     // (measured slower than the register prefetch on B200, kept as an option)
+#endif
+#ifndef QCD_REG_STEP_THREADS
+#define QCD_REG_STEP_THREADS 256
+#endif
+
 constexpr int K_NONE = 0, K_P = 1, K_RX = 2, K_CP = 3, K_CX = 4;
 
 constexpr int RF_RESET = 1;    // episode finished and autoreset is on: state <- e0 / I after this step
@@ -111,7 +134,11 @@ __device__ __forceinline__ void decode_action(const qcd_batch_t& b, double a0, d
   double cr = 1.0, sr = 0.0;
   if (kind == K_P || kind == K_CP || kind == K_RX) {
     const double arg = (kind == K_RX) ? a3 / 2 : a3;           // RXGate: cos/sin(theta/2)
+#if defined(QCD_EXP_NOSINCOS)
+    cr = 1.0 - arg * arg * 0.5; sr = arg;     // EXPERIMENT ONLY (wrong numerics): decode-latency probe
+#else
     sincos(arg, &sr, &cr);
+#endif
   }
   uint32_t ops = e.meta.w & 0xffffu, used = e.meta.w >> 16;
   if (kind != K_NONE) {
@@ -179,27 +206,33 @@ __device__ __forceinline__ double2 reset_amp(bool uc, int eta, int i) {
   return make_double2(one ? 1.0 : 0.0, 0.0);
 }
 
+// Gate arithmetic, written with explicit rounding intrinsics so that every kernel (pair-streaming
+// step, register-resident step, shared-memory replay) produces bit-identical amplitudes.
+// own * e^{i th}, e^{i th} = (cr, sr)
+__device__ __forceinline__ double2 mul_phase(const double2 a, const double cr, const double sr) {
+  return make_double2(__fma_rn(a.x, cr, -__dmul_rn(a.y, sr)), __fma_rn(a.x, sr, __dmul_rn(a.y, cr)));
+}
+// RX row: c*own - i*s*partner  (the same expression for both amplitudes of the pair)
+__device__ __forceinline__ double2 rot_rx(const double2 own, const double2 p, const double c, const double s) {
+  return make_double2(__fma_rn(c, own.x, __dmul_rn(s, p.y)), __fma_rn(c, own.y, -__dmul_rn(s, p.x)));
+}
+
 // The 2x2 butterfly on one amplitude pair; (a0,a1) at (i0, i0|1<<wbit).
 __device__ __forceinline__ void apply_pair(const GateRec& g, int i0, double2& a0, double2& a1) {
   switch (g.kind) {
-    case K_P: {                       // diag(1, e^{i th}) on the w-bit
-      const double re = a1.x * g.cr - a1.y * g.sr, im = a1.x * g.sr + a1.y * g.cr;
-      a1.x = re; a1.y = im;
-    } break;
-    case K_CP: {                      // diag(1,1,1,e^{i th}): both bits set
-      if ((i0 >> g.cbit) & 1) {
-        const double re = a1.x * g.cr - a1.y * g.sr, im = a1.x * g.sr + a1.y * g.cr;
-        a1.x = re; a1.y = im;
-      }
-    } break;
+    case K_P:                         // diag(1, e^{i th}) on the w-bit
+      a1 = mul_phase(a1, g.cr, g.sr);
+      break;
+    case K_CP:                        // diag(1,1,1,e^{i th}): both bits set
+      if ((i0 >> g.cbit) & 1) a1 = mul_phase(a1, g.cr, g.sr);
+      break;
     case K_RX: {                      // [[c, -is], [-is, c]]
-      const double r0 = g.cr * a0.x + g.sr * a1.y, m0 = g.cr * a0.y - g.sr * a1.x;
-      const double r1 = g.sr * a0.y + g.cr * a1.x, m1 = g.cr * a1.y - g.sr * a0.x;
-      a0.x = r0; a0.y = m0; a1.x = r1; a1.y = m1;
+      const double2 n0 = rot_rx(a0, a1, g.cr, g.sr), n1 = rot_rx(a1, a0, g.cr, g.sr);
+      a0 = n0; a1 = n1;
     } break;
-    case K_CX: {                      // swap the pair where the control bit is set
+    case K_CX:                        // swap the pair where the control bit is set
       if ((i0 >> g.cbit) & 1) { const double2 t = a0; a0 = a1; a1 = t; }
-    } break;
+      break;
     default: break;
   }
 }
@@ -212,6 +245,95 @@ __device__ __forceinline__ void metric_acc(const double2 a, const double2 t, dou
   } else {                            // vdot: conj(psi) * target
     ra += a.x * t.x + a.y * t.y;
     rb += a.x * t.y - a.y * t.x;
+  }
+}
+
+// The statistics vector is replicated QCD_STATS_COPIES times (one 128-byte line each) so that the
+// per-warp atomicAdds of a launch spread over many L2 lines instead of serialising on one.
+__device__ __forceinline__ double* stats_slice(const qcd_batch_t& b, const long unit) {
+  return b.stats ? b.stats + (unit & (QCD_STATS_COPIES - 1)) * QCD_STATS_STRIDE : nullptr;
+}
+
+template <bool UC>
+__device__ __forceinline__ void metric_set(const double2 a, const double2 t, double& ra, double& rb) {
+  if (UC) {
+    const double dx = t.x - a.x, dy = t.y - a.y;
+    ra = dx * dx + dy * dy; rb = 0.0;
+  } else {
+    ra = a.x * t.x + a.y * t.y;
+    rb = a.x * t.y - a.y * t.x;
+  }
+}
+
+// Phase 3 of every kernel: finalize (reward shaping), per-env scalar outputs, Monitor latch,
+// auto-reset of the control registers, and the fused K3 statistics reduction.
+// Must be called by ALL threads of the CTA (the statistics use full-warp collectives).
+template <bool UC, int E>
+__device__ __forceinline__ void phase3(const qcd_batch_t& b, const qcd_tape_out_t& out, EnvCtl& e,
+                                     const bool ctl, const long cenv, const int t, const int T,
+                                     const long N, const int tid, const double2 r, const bool have_metric,
+                                     double* __restrict__ stats) {
+  const bool autoreset = b.flags & QCD_F_AUTORESET;
+  int st_fin = 0, st_ok = 0, st_bad = 0, st_trunc = 0, st_l = 0, st_d = 0, st_o = 0, st_q = 0;
+  double st_r = 0.0, st_m = 0.0, st_c = 0.0;
+  if (ctl) {
+    const StepOut o = finalize_step<UC>(b, e, r.x, r.y, have_metric);
+    const bool done = (e.status == QCD_ST_OK) && (e.term || e.trunc);
+    if (out.reward) out.reward[(long)t * N + cenv] = o.reward;
+    if (out.metric) out.metric[(long)t * N + cenv] = o.metric;
+    if (out.cost) out.cost[(long)t * N + cenv] = o.cost;
+    if (out.depth) out.depth[(long)t * N + cenv] = e.depth;
+    if (out.terminated) out.terminated[(long)t * N + cenv] = e.term;
+    if (out.truncated) out.truncated[(long)t * N + cenv] = e.trunc;
+    if (out.status) out.status[(long)t * N + cenv] = (int8_t)e.status;
+    if (t == T - 1) {
+      b.reward[cenv] = o.reward; b.metric[cenv] = o.metric; b.cost[cenv] = o.cost;
+      b.depth[cenv] = e.depth; b.operations[cenv] = e.ops; b.used_wires[cenv] = e.used_cnt;
+      b.terminated[cenv] = e.term; b.truncated[cenv] = e.trunc; b.status[cenv] = (int8_t)e.status;
+    }
+    st_ok = e.status == QCD_ST_OK; st_bad = !st_ok;
+    if (done) {
+      st_fin = 1; st_trunc = e.trunc; st_l = e.ep_len; st_d = e.depth; st_o = e.ops; st_q = e.used_cnt;
+      st_r = e.ep_ret; st_m = o.metric; st_c = o.cost;
+      if (b.episode_return) { b.episode_return[cenv] = e.ep_ret; b.episode_length[cenv] = e.ep_len; }
+      if (autoreset) {                          // env.py:117-121 fused
+        e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
+      }
+    }
+  }
+  // Fused K3: Monitor episode fields + termination histogram summed over the warp, then one
+  // atomicAdd per non-zero field per warp of control threads (warp-uniform branch).
+  if (stats != nullptr && (tid >> 5) <= ((E - 1) >> 5)) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n_fin = __reduce_add_sync(FULL, st_fin);
+    const int n_ok = __reduce_add_sync(FULL, st_ok);
+    const int n_bad = __reduce_add_sync(FULL, st_bad);
+    if (n_fin) {
+      const int n_trunc = __reduce_add_sync(FULL, st_trunc);
+      const int s_l = __reduce_add_sync(FULL, st_l), s_d = __reduce_add_sync(FULL, st_d);
+      const int s_o = __reduce_add_sync(FULL, st_o), s_q = __reduce_add_sync(FULL, st_q);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        st_r += __shfl_xor_sync(FULL, st_r, off);
+        st_m += __shfl_xor_sync(FULL, st_m, off);
+        st_c += __shfl_xor_sync(FULL, st_c, off);
+      }
+      if ((tid & 31) == 0) {
+        atomicAdd(stats + QCD_STAT_EPISODES, (double)n_fin);
+        if (b.ep_return) { atomicAdd(stats + QCD_STAT_SUM_R, st_r); atomicAdd(stats + QCD_STAT_SUM_L, (double)s_l); }
+        atomicAdd(stats + QCD_STAT_SUM_D, (double)s_d);
+        atomicAdd(stats + QCD_STAT_SUM_O, (double)s_o);
+        atomicAdd(stats + QCD_STAT_SUM_Q, (double)s_q);
+        atomicAdd(stats + QCD_STAT_SUM_M, st_m);
+        atomicAdd(stats + QCD_STAT_SUM_C, st_c);
+        if (n_fin - n_trunc) atomicAdd(stats + QCD_STAT_N_DONE, (double)(n_fin - n_trunc));
+        if (n_trunc) atomicAdd(stats + QCD_STAT_N_DEPTH, (double)n_trunc);
+      }
+    }
+    if ((tid & 31) == 0) {
+      if (n_ok) atomicAdd(stats + QCD_STAT_STEPS, (double)n_ok);
+      if (n_bad) atomicAdd(stats + QCD_STAT_BAD_ACTIONS, (double)n_bad);
+    }
   }
 }
 
@@ -248,7 +370,6 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
   const bool ctl = tid < E && env0 + tid < N;     // this thread is the control thread of env0+tid
   const long cenv = env0 + tid;
   const bool per_env_tgt = b.flags & QCD_F_TARGET_PER_ENV;
-  const bool autoreset = b.flags & QCD_F_AUTORESET;
 
   double2* gstate = reinterpret_cast<double2*>(b.state);
   const double2* tgt = reinterpret_cast<const double2*>(b.target) + (per_env_tgt && gact ? genv * S : 0);
@@ -356,70 +477,9 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
       s_red[0] = make_double2(xa, xb);            // read below by the same thread (tid 0 is ctl)
     }
 
-    // ================= phase 3: per-env finalize + scalar outputs
-    int st_fin = 0, st_ok = 0, st_bad = 0, st_trunc = 0, st_l = 0, st_d = 0, st_o = 0, st_q = 0;
-    double st_r = 0.0, st_m = 0.0, st_c = 0.0;
-    if (ctl) {
-      const double2 r = s_red[tid];
-      const bool have_metric = s_rec[tid].flags & RF_METRIC;
-      const StepOut o = finalize_step<UC>(b, e, r.x, r.y, have_metric);
-      const bool done = (e.status == QCD_ST_OK) && (e.term || e.trunc);
-      if (out.reward) out.reward[(long)t * N + cenv] = o.reward;
-      if (out.metric) out.metric[(long)t * N + cenv] = o.metric;
-      if (out.cost) out.cost[(long)t * N + cenv] = o.cost;
-      if (out.depth) out.depth[(long)t * N + cenv] = e.depth;
-      if (out.terminated) out.terminated[(long)t * N + cenv] = e.term;
-      if (out.truncated) out.truncated[(long)t * N + cenv] = e.trunc;
-      if (out.status) out.status[(long)t * N + cenv] = (int8_t)e.status;
-      if (t == T - 1) {
-        b.reward[cenv] = o.reward; b.metric[cenv] = o.metric; b.cost[cenv] = o.cost;
-        b.depth[cenv] = e.depth; b.operations[cenv] = e.ops; b.used_wires[cenv] = e.used_cnt;
-        b.terminated[cenv] = e.term; b.truncated[cenv] = e.trunc; b.status[cenv] = (int8_t)e.status;
-      }
-      st_ok = e.status == QCD_ST_OK; st_bad = !st_ok;
-      if (done) {
-        st_fin = 1; st_trunc = e.trunc; st_l = e.ep_len; st_d = e.depth; st_o = e.ops; st_q = e.used_cnt;
-        st_r = e.ep_ret; st_m = o.metric; st_c = o.cost;
-        if (b.episode_return) { b.episode_return[cenv] = e.ep_ret; b.episode_length[cenv] = e.ep_len; }
-        if (autoreset) {                          // env.py:117-121 fused
-          e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
-        }
-      }
-    }
-    // Fused K3: Monitor episode fields + termination histogram summed over the warp, then one
-    // atomicAdd per non-zero field per warp of control threads (warp-uniform branch).
-    if (b.stats != nullptr && (tid >> 5) <= ((E - 1) >> 5)) {
-      constexpr unsigned FULL = 0xffffffffu;
-      const int n_fin = __reduce_add_sync(FULL, st_fin);
-      const int n_ok = __reduce_add_sync(FULL, st_ok);
-      const int n_bad = __reduce_add_sync(FULL, st_bad);
-      if (n_fin) {
-        const int n_trunc = __reduce_add_sync(FULL, st_trunc);
-        const int s_l = __reduce_add_sync(FULL, st_l), s_d = __reduce_add_sync(FULL, st_d);
-        const int s_o = __reduce_add_sync(FULL, st_o), s_q = __reduce_add_sync(FULL, st_q);
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          st_r += __shfl_xor_sync(FULL, st_r, off);
-          st_m += __shfl_xor_sync(FULL, st_m, off);
-          st_c += __shfl_xor_sync(FULL, st_c, off);
-        }
-        if ((tid & 31) == 0) {
-          atomicAdd(b.stats + QCD_STAT_EPISODES, (double)n_fin);
-          if (b.ep_return) { atomicAdd(b.stats + QCD_STAT_SUM_R, st_r); atomicAdd(b.stats + QCD_STAT_SUM_L, (double)s_l); }
-          atomicAdd(b.stats + QCD_STAT_SUM_D, (double)s_d);
-          atomicAdd(b.stats + QCD_STAT_SUM_O, (double)s_o);
-          atomicAdd(b.stats + QCD_STAT_SUM_Q, (double)s_q);
-          atomicAdd(b.stats + QCD_STAT_SUM_M, st_m);
-          atomicAdd(b.stats + QCD_STAT_SUM_C, st_c);
-          if (n_fin - n_trunc) atomicAdd(b.stats + QCD_STAT_N_DONE, (double)(n_fin - n_trunc));
-          if (n_trunc) atomicAdd(b.stats + QCD_STAT_N_DEPTH, (double)n_trunc);
-        }
-      }
-      if ((tid & 31) == 0) {
-        if (n_ok) atomicAdd(b.stats + QCD_STAT_STEPS, (double)n_ok);
-        if (n_bad) atomicAdd(b.stats + QCD_STAT_BAD_ACTIONS, (double)n_bad);
-      }
-    }
+    // ================= phase 3: per-env finalize + scalar outputs + fused episode statistics
+    phase3<UC, E>(b, out, e, ctl, cenv, t, T, N, tid, ctl ? s_red[tid] : make_double2(0.0, 0.0),
+                  ctl && (s_rec[tid].flags & RF_METRIC), stats_slice(b, blockIdx.x));
     // No barrier needed here: s_rec[tid] / s_red[tid] are re-written in phase 1 / phase 2 of step
     // t+1 only after their phase-2 / phase-3 readers of step t have passed the barrier above /
     // are the writing thread itself.
@@ -435,6 +495,447 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
     const long lim = (N - env0 < E ? N - env0 : E) * (long)S;
     for (long i = tid; i < lim; i += NT) gstate[base + i] = s_tile[i];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident STEP kernel for small states (S <= 256 amplitudes, i.e. <= 4 KiB per env).
+//
+// The pair-streaming kernel above cannot issue its state loads before the action is decoded (the
+// pair addresses depend on the wire), which serialises two DRAM latencies + a sincos behind a CTA
+// barrier.  Here the ownership of amplitudes is FIXED: lane l of the env's group of L lanes owns
+// amplitudes i = l + L*j (j < V), so every state / target load is issued at kernel entry, fully
+// coalesced (the L lanes of a group read L*16 contiguous bytes per j), and overlaps the decode.
+// The butterfly partner of amplitude i for wire bit w is then either in the same lane
+// (w >= log2 L: register j ^ 2^(w-log2 L), chosen with selects) or in lane l ^ 2^w (one shuffle).
+template <int LOG2S, bool UC, int LOG2L, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+step_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32) {
+  constexpr int S = 1 << LOG2S, L = 1 << LOG2L, E = NT / L, V = S / L;
+  constexpr int LOG2V = LOG2S - LOG2L;
+  static_assert(L <= 32 && V >= 1 && V <= 16, "register-resident step: group within a warp");
+  constexpr unsigned FULL = 0xffffffffu;
+
+  __shared__ GateRec s_rec[E];
+  __shared__ double2 s_red[E];
+
+  const int tid = threadIdx.x;
+  const long env0 = (long)blockIdx.x * E;
+  const long N = b.n_envs;
+  const int grp = tid >> LOG2L, lane = tid & (L - 1);
+  const long genv = env0 + grp;
+  const bool gact = genv < N;
+  const bool ctl = tid < E && env0 + tid < N;
+  const long cenv = env0 + tid;
+
+  // ---- all state / target loads first: they do not depend on the action
+  double2* st = reinterpret_cast<double2*>(b.state) + (gact ? genv * S : 0);
+  const double2* tg = reinterpret_cast<const double2*>(b.target) +
+                      (((b.flags & QCD_F_TARGET_PER_ENV) && gact) ? genv * S : 0);
+  double2 x[V], tv[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) x[j] = gact ? st[lane + L * j] : make_double2(0.0, 0.0);
+#pragma unroll
+  for (int j = 0; j < V; ++j) tv[j] = gact ? __ldg(tg + lane + L * j) : make_double2(0.0, 0.0);
+
+  // ---- phase 1: per-env scalar decode by the control threads (one env per thread)
+  EnvCtl e;
+  e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
+  if (ctl) {
+    double a0, a1, a2, a3;
+    load_action(actions, act_f32, cenv, a0, a1, a2, a3);
+    e.meta = reinterpret_cast<const uint4*>(b.meta)[cenv];
+    if (b.last) { const double2 l2 = reinterpret_cast<const double2*>(b.last)[cenv]; e.last_m = l2.x; e.last_c = l2.y; }
+    if (b.ep_return) { e.ep_ret = b.ep_return[cenv]; e.ep_len = b.ep_length[cenv]; }
+    GateRec rec;
+    decode_action(b, a0, a1, a2, a3, e, rec);
+    rec.flags |= RF_METRIC | RF_LAST;
+    s_rec[tid] = rec;
+  }
+  __syncthreads();
+
+  // ---- phase 2: butterflies in registers
+  GateRec g;
+  if (gact) g = s_rec[grp];
+  else { g.kind = K_NONE; g.wbit = 0; g.cbit = 0; g.flags = 0; g.cr = 1.0; g.sr = 0.0; }
+  const bool reset = g.flags & RF_RESET;
+  const bool lane_bit = g.wbit < LOG2L;                       // partner lives in another lane
+  const int src_lane = (tid & 31) ^ (lane_bit ? (1 << g.wbit) : 0);
+  const int jb = lane_bit ? 0 : (g.wbit - LOG2L);             // register bit of the wire otherwise
+  double2 y[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    // in-lane candidate: x[j ^ (1 << jb)] (selects over the compile-time register bits)
+    double2 p = x[j];
+    if (LOG2V > 0) {
+#pragma unroll
+      for (int bit = 0; bit < LOG2V; ++bit) {
+        const double2 cand = x[j ^ (1 << bit)];
+        const bool take = !lane_bit && jb == bit;
+        p.x = take ? cand.x : p.x; p.y = take ? cand.y : p.y;
+      }
+    }
+    // cross-lane partner (identity shuffle when the wire is a register bit); all lanes take part
+    p.x = __shfl_sync(FULL, p.x, src_lane);
+    p.y = __shfl_sync(FULL, p.y, src_lane);
+    const int i = lane + L * j;
+    const bool bw = (i >> g.wbit) & 1, bc = (i >> g.cbit) & 1;
+    double2 v = x[j];
+    switch (g.kind) {
+      case K_P:  if (bw) v = mul_phase(v, g.cr, g.sr); break;
+      case K_CP: if (bw && bc) v = mul_phase(v, g.cr, g.sr); break;
+      case K_RX: v = rot_rx(v, p, g.cr, g.sr); break;
+      case K_CX: if (bc) v = p; break;
+      default: break;
+    }
+    y[j] = v;
+  }
+  double ra = 0.0, rb = 0.0;
+#pragma unroll
+  for (int j = 0; j < V; ++j) metric_acc<UC>(y[j], tv[j], ra, rb);
+#pragma unroll
+  for (int off = L / 2; off >= 1; off >>= 1) {
+    ra += __shfl_xor_sync(FULL, ra, off);
+    rb += __shfl_xor_sync(FULL, rb, off);
+  }
+  if (lane == 0 && gact) s_red[grp] = make_double2(ra, rb);
+
+  if (gact) {
+    float* ob = b.obs ? b.obs + genv * b.obs_stride : nullptr;
+    float* fob = (b.final_obs && reset) ? b.final_obs + genv * b.obs_stride : nullptr;
+    const bool wr_state = g.kind != K_NONE || reset;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int i = lane + L * j;
+      if (fob) { fob[i] = (float)y[j].x; fob[S + i] = (float)y[j].y; }
+      const double2 v = reset ? reset_amp(UC, b.n_qubits, i) : y[j];
+      if (wr_state) st[i] = v;
+      if (ob) { ob[i] = (float)v.x; ob[S + i] = (float)v.y; }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3
+  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  phase3<UC, E>(b, none, e, ctl, cenv, 0, 1, N, tid, ctl ? s_red[tid] : make_double2(0.0, 0.0), ctl,
+                stats_slice(b, blockIdx.x));
+  if (ctl) {
+    reinterpret_cast<uint4*>(b.meta)[cenv] = e.meta;
+    if (b.last) reinterpret_cast<double2*>(b.last)[cenv] = make_double2(e.last_m, e.last_c);
+    if (b.ep_return) { b.ep_return[cenv] = e.ep_ret; b.ep_length[cenv] = e.ep_len; }
+  }
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier helpers: 1-D bulk copies of a warp's contiguous state tile
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();    // never hang the GPU on a lost transaction
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int LOG2S, int TE, bool STAGE>
+struct WarpCfg {
+  static constexpr int S = 1 << LOG2S;
+  static constexpr int LOG2L = LOG2S < 5 ? LOG2S : 5, L = 1 << LOG2L;
+  static constexpr int V = S / L, LOG2V = LOG2S - LOG2L;
+  static constexpr int G = 32 / L, LOG2G = 5 - LOG2L;       // envs per round
+  static constexpr int R = TE / G;                         // rounds per tile
+  static constexpr int C = R < 8 ? R : 8;                  // rounds per reduction chunk
+  static constexpr int PF0 = V == 1 ? 4 : (V <= 4 ? 2 : 1);
+  static constexpr int PF = STAGE ? 1 : (PF0 < C ? PF0 : C);   // rounds of state in flight in registers
+  static constexpr int ROW = 36;                           // double2 slots per scratch row
+  static constexpr int SUMS = C * G, P = 32 / SUMS, VAL = L / P;
+  static constexpr int TILE = STAGE ? TE * S : 0;          // double2 slots of the staged state tile
+  // per-warp smem: [tile][partials C*ROW][gate (cr,sr) 32][gate word 32 ints = 8 slots][mbarrier 8 slots]
+  static constexpr int WARP_SLOTS = TILE + C * ROW + 32 + 8 + 8;
+  static_assert(TE >= G && TE <= 32 && R >= 1 && C % PF == 0 && R % C == 0 && V <= 8 && P >= 1 && VAL >= 1, "tile shape");
+};
+
+// gate word handed from the decode lane to the rounds:
+//   [2:0] kind  [3] reset  [8:4] lane xor mask of the butterfly partner (0: partner in-lane)
+//   [10:9] 1 + register bit of the wire when the partner is in-lane (0 otherwise)
+//   [18:11] 1<<wbit as a mask over the amplitude index  [26:19] 1<<cbit likewise
+template <int LOG2L>
+__device__ __forceinline__ int pack_gate(const GateRec& g) {
+  const bool in_lane = g.wbit >= LOG2L;
+  const int xm = in_lane ? 0 : (1 << g.wbit);
+  const int jsel = in_lane ? (1 + g.wbit - LOG2L) : 0;
+  return g.kind | ((g.flags & RF_RESET) ? 8 : 0) | (xm << 4) | (jsel << 9) | ((1 << g.wbit) << 11) |
+         ((1 << g.cbit) << 19);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-autonomous STEP kernel for small states (S <= 256 amplitudes): the production step path.
+//
+// ncu on the two kernels above (profiles/r01_*): 30-40 % of all warp samples sit at the CTA barrier
+// behind the single decode warp, issue utilisation is 24-36 %, and the launch is latency- not
+// HBM-bound.  Here a WARP owns a tile of TE consecutive envs and never synchronises with anyone:
+//   state tile   : STAGE: lane 0 issues ONE cp.async.bulk (TMA) of the tile's TE*S*16 contiguous
+//                  bytes into shared memory, completion on an mbarrier, before anything else, so the
+//                  whole tile is in flight during the scalar phase; the rounds then work in place in
+//                  smem and one bulk store writes the tile back.  !STAGE: register prefetch PF rounds
+//                  ahead with plain coalesced LDG.128/STG.128;
+//   scalar phase : lane e < TE decodes env e of the tile (coalesced scalar I/O) and leaves the gate
+//                  (one packed word + cos/sin) in the warp's smem;
+//   rounds       : the tile's states are processed in R rounds of G = 32/L envs, L = min(32,S) lanes
+//                  per env, V = S/L amplitudes per lane (amplitude i = li + L*j).  The butterfly
+//                  partner is one shuffle away (wire bit < log2 L) or in a sibling register;
+//   metric sums  : per-lane partial sums go to a per-warp smem scratch, 8 rounds at a time, and are
+//                  reduced transposed (each lane adds 8 values + <=2 shuffles) instead of a 5-step
+//                  butterfly per env; the sum returns to the env's decode lane;
+//   finalize     : lane e shapes the reward and writes env e's scalars (coalesced), statistics are
+//                  reduced with REDUX/shuffles and one atomicAdd per field per warp.
+template <int LOG2S, bool UC, int WARPS, int TE, bool STAGE, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32) {
+  using W = WarpCfg<LOG2S, TE, STAGE>;
+  constexpr int S = W::S, LOG2L = W::LOG2L, L = W::L, V = W::V, LOG2V = W::LOG2V, G = W::G, LOG2G = W::LOG2G;
+  constexpr int R = W::R, C = W::C, PF = W::PF, ROW = W::ROW, SUMS = W::SUMS, P = W::P, VAL = W::VAL;
+  constexpr unsigned FULL = 0xffffffffu;
+
+  extern __shared__ __align__(128) double2 s_dyn[];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long tile = (long)blockIdx.x * WARPS + warp;
+  const long N = b.n_envs;
+  const long env_base = tile * TE;
+  if (env_base >= N) return;                      // whole warp; no CTA-level synchronisation below
+  const int n_valid = (int)((N - env_base) < TE ? (N - env_base) : TE);
+  const int li = lane & (L - 1), gi = lane >> LOG2L;
+  double2* wsm = s_dyn + (long)warp * W::WARP_SLOTS;
+  double2* stile = wsm;                           // [TE*S] staged states (STAGE)
+  double2* part = wsm + W::TILE;                  // [C*ROW] partial metric sums
+  double2* s_cs = part + C * ROW;                 // [32] (cos, sin) of each env's gate
+  int* s_pk = reinterpret_cast<int*>(s_cs + 32);  // [32] packed gate word
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_cs + 32 + 8);
+  double2* tstate = reinterpret_cast<double2*>(b.state) + env_base * S;
+  const double2* tgt = reinterpret_cast<const double2*>(b.target);   // shared target (per-env targets
+                                                                     // take the pair-streaming kernel)
+  if (STAGE) {                                    // the tile goes in flight first
+    if (lane == 0) {
+      mbar_init(mbar, 1);
+      bulk_load(stile, tstate, (uint32_t)(n_valid * S * sizeof(double2)), mbar);
+    }
+  }
+
+  // ---- scalar loads of env_base + lane (and, !STAGE, the state of the first PF rounds)
+  const long env = env_base + lane;
+  const bool ctl = lane < TE && env < N;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  EnvCtl e;
+  e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
+  if (ctl) {
+    load_action(actions, act_f32, env, a0, a1, a2, a3);
+    e.meta = reinterpret_cast<const uint4*>(b.meta)[env];
+    if (b.last) { const double2 l2 = reinterpret_cast<const double2*>(b.last)[env]; e.last_m = l2.x; e.last_c = l2.y; }
+    if (b.ep_return) { e.ep_ret = b.ep_return[env]; e.ep_len = b.ep_length[env]; }
+  }
+  // per-lane pointers of round 0; round r is a constant G*S (state) / G*stride (obs) further on
+  const long gstride = (long)G * b.obs_stride;
+  double2* sp = tstate + gi * S + li;
+  const double2* stp = stile + gi * S + li;
+  float* op = b.obs ? b.obs + (env_base + gi) * b.obs_stride + li : nullptr;
+  float* fp = b.final_obs ? b.final_obs + (env_base + gi) * b.obs_stride + li : nullptr;
+
+  double2 buf[PF][V];
+  if (!STAGE) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const bool ok = u * G + gi < n_valid;
+#pragma unroll
+      for (int j = 0; j < V; ++j) buf[u][j] = ok ? sp[u * G * S + L * j] : make_double2(0.0, 0.0);
+    }
+  }
+  double2 tv[V];
+  double rv[V];                                   // reset amplitude (e0 / identity) of this lane's slots
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    tv[j] = __ldg(tgt + li + L * j);
+    rv[j] = reset_amp(UC, b.n_qubits, li + L * j).x;
+  }
+
+  // ---- scalar phase: decode (env.py:90-100,129,112)
+  {
+    int pk = 0;
+    double2 cs = make_double2(1.0, 0.0);
+    if (ctl) {
+      GateRec rec;
+      decode_action(b, a0, a1, a2, a3, e, rec);
+      pk = pack_gate<LOG2L>(rec);
+      cs = make_double2(rec.cr, rec.sr);
+    }
+    s_cs[lane] = cs; s_pk[lane] = pk;
+  }
+  __syncwarp();
+  if (STAGE) mbar_wait(mbar, 0);                  // tile landed
+
+  double2 mysum = make_double2(0.0, 0.0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < R; c0 += C) {
+#pragma unroll
+    for (int rr = 0; rr < C; rr += PF) {
+      double2 cur[PF][V];
+      if (STAGE) {
+        const bool ok = (c0 + rr) * G + gi < n_valid;
+#pragma unroll
+        for (int j = 0; j < V; ++j) cur[0][j] = ok ? stp[rr * G * S + L * j] : make_double2(0.0, 0.0);
+      } else {
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+#pragma unroll
+          for (int j = 0; j < V; ++j) cur[u][j] = buf[u][j];
+        if (c0 + rr + PF < R) {                   // keep the next PF rounds in flight
+#pragma unroll
+          for (int u = 0; u < PF; ++u) {
+            const bool ok = (c0 + rr + PF + u) * G + gi < n_valid;
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              buf[u][j] = ok ? sp[(rr + PF + u) * G * S + L * j] : make_double2(0.0, 0.0);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int k = rr + u;                     // round within the chunk (compile-time)
+        const int src = (c0 + k) * G + gi;        // decode lane / tile-local env of this group
+        const double2 cs = s_cs[src];
+        const int pk = s_pk[src];
+        const int kind = pk & 7;
+        const bool reset = pk & 8;
+        const unsigned wm = (pk >> 11) & 0xffu, cm = (pk >> 19) & 0xffu;
+        const bool act = src < n_valid;
+        // butterfly partner: only RX and CX read it; the shuffle needs the whole warp
+        const bool need_p = kind == K_RX || kind == K_CX;
+        double2 pv[V];
+        if (__any_sync(FULL, need_p)) {
+          const int src_lane = lane ^ ((pk >> 4) & 31);
+          const int jsel = (pk >> 9) & 3;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            double2 p = cur[u][j];
+            if (LOG2V > 0) {
+#pragma unroll
+              for (int bit = 0; bit < LOG2V; ++bit) {
+                const double2 cand = cur[u][j ^ (1 << bit)];
+                const bool take = jsel == bit + 1;
+                p.x = take ? cand.x : p.x; p.y = take ? cand.y : p.y;
+              }
+            }
+            pv[j].x = __shfl_sync(FULL, p.x, src_lane);
+            pv[j].y = __shfl_sync(FULL, p.y, src_lane);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < V; ++j) pv[j] = cur[u][j];
+        }
+        double ra, rb;
+        double2 y[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const unsigned i = li + L * j;
+          const bool bw = i & wm, bc = i & cm;
+          double2 v = cur[u][j];
+          switch (kind) {
+            case K_P:  if (bw) v = mul_phase(v, cs.x, cs.y); break;
+            case K_CP: if (bw && bc) v = mul_phase(v, cs.x, cs.y); break;
+            case K_RX: v = rot_rx(v, pv[j], cs.x, cs.y); break;
+            case K_CX: if (bc) v = pv[j]; break;
+            default: break;
+          }
+          y[j] = v;
+          if (j == 0) metric_set<UC>(v, tv[j], ra, rb); else metric_acc<UC>(v, tv[j], ra, rb);
+        }
+        part[k * ROW + lane] = make_double2(ra, rb);
+        if (act) {
+          if (reset && fp) {
+            float* f = fp + (long)(c0 + k) * gstride;
+#pragma unroll
+            for (int j = 0; j < V; ++j) { f[L * j] = (float)y[j].x; f[S + L * j] = (float)y[j].y; }
+          }
+          if (kind != K_NONE || reset) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const double2 v = reset ? make_double2(rv[j], 0.0) : y[j];
+              if (STAGE) stile[src * S + li + L * j] = v; else sp[k * G * S + L * j] = v;
+            }
+          }
+          if (op) {
+            float* o = op + k * gstride;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              o[L * j] = reset ? (float)rv[j] : (float)y[j].x;
+              o[S + L * j] = reset ? 0.0f : (float)y[j].y;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- transposed reduction of the chunk: sum id s = k*G + g2 (round k of the chunk, group g2)
+    {
+      const int sidx = lane / P, prt = lane % P;
+      const int k = sidx >> LOG2G, g2 = sidx & (G - 1);
+      const double2* row = part + k * ROW + g2 * L + prt;
+      double xa = 0.0, xb = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < VAL; ++jj) {
+        const double2 q = row[P * ((jj + g2) & (VAL - 1))];
+        xa += q.x; xb += q.y;
+      }
+#pragma unroll
+      for (int off = P / 2; off >= 1; off >>= 1) {
+        xa += __shfl_xor_sync(FULL, xa, off);
+        xb += __shfl_xor_sync(FULL, xb, off);
+      }
+      // env (c0*G + s) of the tile is decoded by lane c0*G + s: hand the sum over
+      const int want = lane - c0 * G;
+      const int from = (want & (SUMS - 1)) * P;
+      const double va = __shfl_sync(FULL, xa, from), vb = __shfl_sync(FULL, xb, from);
+      if (want >= 0 && want < SUMS) mysum = make_double2(va, vb);
+    }
+    __syncwarp();
+    sp += C * G * S; stp += C * G * S;
+    if (op) op += C * gstride;
+  }
+
+  if (STAGE) {                                    // one bulk store of the whole (modified) tile
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) bulk_store(tstate, stile, (uint32_t)(n_valid * S * sizeof(double2)));
+  }
+
+  // ---- finalize + scalar outputs + fused statistics
+  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  phase3<UC, 32>(b, none, e, ctl, env, 0, 1, N, lane, mysum, ctl, stats_slice(b, tile));
+  if (ctl) {
+    reinterpret_cast<uint4*>(b.meta)[env] = e.meta;
+    if (b.last) reinterpret_cast<double2*>(b.last)[env] = make_double2(e.last_m, e.last_c);
+    if (b.ep_return) { b.ep_return[env] = e.ep_ret; b.ep_length[env] = e.ep_len; }
+  }
+  if (STAGE && lane == 0) bulk_store_wait_read(); // smem must outlive the bulk store's reads
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,7 +1004,7 @@ stats_kernel(const qcd_batch_t b, double* __restrict__ stats) {
   if (threadIdx.x < QCD_STATS_LEN) {
     double acc = 0.0;
     for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) acc += s_part[wv][threadIdx.x];
-    if (acc != 0.0) atomicAdd(stats + threadIdx.x, acc);
+    if (acc != 0.0) atomicAdd(stats + (blockIdx.x & (QCD_STATS_COPIES - 1)) * QCD_STATS_STRIDE + threadIdx.x, acc);
   }
 }
 
@@ -521,9 +1022,51 @@ struct Launch {
   static constexpr int LOG2L = ilog2(L);
   static constexpr int E = NT / L;
   static constexpr size_t SMEM = STAGED ? (size_t)E * S * sizeof(double2) : 0;
+  static constexpr bool REG = !STAGED && LOG2S <= QCD_REG_STEP_MAX_LOG2S;   // register-resident step
 
   static int run(const qcd_batch_t& b, const void* actions, int act_f32, int T,
                  const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream) {
+    if constexpr (REG && QCD_STEP_IMPL == 2) {
+      if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
+      constexpr int W = QCD_WARP_STEP_WARPS;
+      constexpr int G = S < 32 ? 32 / S : 1;
+      constexpr int TE0 = QCD_WARP_STEP_TILE > 0 ? QCD_WARP_STEP_TILE : clampi(8192 / (S * 16), 8, 32);
+      constexpr int TE = TE0 < G ? G : TE0;
+      constexpr bool STG = QCD_WARP_STEP_STAGE && (TE * S * 16 <= 16384);
+      using WC = WarpCfg<LOG2S, TE, STG>;
+      constexpr size_t smem = (size_t)W * WC::WARP_SLOTS * sizeof(double2);
+      auto kern = step_warp_kernel<LOG2S, UC, W, TE, STG, QCD_WARP_STEP_MINB>;
+      static bool attr_done[64] = {false};        // per device; set outside of any stream capture path
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (smem > 48 * 1024 && !attr_done[dev & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        attr_done[dev & 63] = true;
+      }
+      const long tiles = ((long)b.n_envs + TE - 1) / TE;
+      const unsigned grid = (unsigned)((tiles + W - 1) / W);
+      kern<<<grid, W * 32, smem, stream>>>(b, actions, act_f32);
+      return (int)cudaGetLastError();
+    } else if constexpr (REG && QCD_STEP_IMPL == 1) {
+      constexpr int RNT = QCD_REG_STEP_THREADS;
+      constexpr int RL = clampi(S / 4, 1, 32);                // V = 4 amplitudes per lane (8 at S=256)
+      constexpr int RE = RNT / RL;
+#ifdef QCD_REG_MINB
+      constexpr int MINB = (S / RL) <= 4 ? QCD_REG_MINB : (512 / RNT);
+#else
+      constexpr int MINB = (S / RL) <= 4 ? (1024 / RNT) : (512 / RNT);
+#endif
+      const unsigned grid = (unsigned)((b.n_envs + RE - 1) / RE);
+      step_reg_kernel<LOG2S, UC, ilog2(RL), RNT, MINB><<<grid, RNT, 0, stream>>>(b, actions, act_f32);
+      return (int)cudaGetLastError();
+    } else {
+      return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
+    }
+  }
+
+  static int run_pair(const qcd_batch_t& b, const void* actions, int act_f32, int T,
+                      const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream) {
     auto kern = qcd_kernel<LOG2S, UC, STAGED, LOG2L, NT>;
     if (SMEM > 48 * 1024) {
       cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);

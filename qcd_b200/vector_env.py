@@ -154,7 +154,7 @@ class CircuitDesignerVectorEnv:
     """Running sums as a dict (synchronises)."""
     vec = self.batch.stats.cpu().numpy().copy()
     if reset:
-      self.batch.stats.zero_()
+      self.batch.zero_stats()
     return dict(zip(_lib.STAT_NAMES, vec.tolist()))
 
   def close(self):
