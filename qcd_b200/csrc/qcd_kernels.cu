@@ -43,10 +43,13 @@ namespace qcd {
 #define QCD_STEP_IMPL 2                // small-S step path: 0 pair-streaming, 1 CTA register-resident, 2 warp-autonomous
 #endif
 #ifndef QCD_WARP_STEP_WARPS
-#define QCD_WARP_STEP_WARPS 4
+#define QCD_WARP_STEP_WARPS 1           // warps per CTA (each warp is autonomous; 1 balances best across 148 SMs)
 #endif
 #ifndef QCD_WARP_STEP_MINB
-#define QCD_WARP_STEP_MINB 4
+#define QCD_WARP_STEP_MINB 16          // min CTAs per SM for __launch_bounds__ (caps registers at 128)
+#endif
+#ifndef QCD_WARP_UNROLL_CHUNKS
+#define QCD_WARP_UNROLL_CHUNKS 0
 #endif
 #ifndef QCD_WARP_STEP_TILE
 #define QCD_WARP_STEP_TILE 32          // envs per warp tile (0 = 8 KiB of state per tile, clamped to 8..32)
@@ -793,7 +796,11 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   if (STAGE) mbar_wait(mbar, 0);                  // tile landed
 
   double2 mysum = make_double2(0.0, 0.0);
+#if QCD_WARP_UNROLL_CHUNKS
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int c0 = 0; c0 < R; c0 += C) {
 #pragma unroll
     for (int rr = 0; rr < C; rr += PF) {
@@ -870,27 +877,27 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
         }
         part[k * ROW + lane] = make_double2(ra, rb);
         if (act) {
-          if (reset && fp) {
-            float* f = fp + (long)(c0 + k) * gstride;
+          if (reset) {                            // episode over: terminal obs out, e0 / I in
+            if (fp) {
+              float* f = fp + (long)(c0 + k) * gstride;
 #pragma unroll
-            for (int j = 0; j < V; ++j) { f[L * j] = (float)y[j].x; f[S + L * j] = (float)y[j].y; }
-          }
-          if (kind != K_NONE || reset) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              const double2 v = reset ? make_double2(rv[j], 0.0) : y[j];
-              if (STAGE) stile[src * S + li + L * j] = v; else sp[k * G * S + L * j] = v;
+              for (int j = 0; j < V; ++j) { f[L * j] = (float)y[j].x; f[S + L * j] = (float)y[j].y; }
             }
-          }
-          if (op) {
-            float* o = op + k * gstride;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-              o[L * j] = reset ? (float)rv[j] : (float)y[j].x;
-              o[S + L * j] = reset ? 0.0f : (float)y[j].y;
+              const double2 v = make_double2(rv[j], 0.0);
+              if (STAGE) stile[src * S + li + L * j] = v; else sp[k * G * S + L * j] = v;
+              if (op) { op[L * j] = (float)rv[j]; op[S + L * j] = 0.0f; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              if (kind != K_NONE) { if (STAGE) stile[src * S + li + L * j] = y[j]; else sp[k * G * S + L * j] = y[j]; }
+              if (op) { op[L * j] = (float)y[j].x; op[S + L * j] = (float)y[j].y; }
             }
           }
         }
+        if (op) op += gstride;
       }
     }
     __syncwarp();
@@ -918,7 +925,6 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
     }
     __syncwarp();
     sp += C * G * S; stp += C * G * S;
-    if (op) op += C * gstride;
   }
 
   if (STAGE) {                                    // one bulk store of the whole (modified) tile
