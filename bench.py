@@ -44,6 +44,8 @@ WORKLOADS = {
     'sp-random12': ('SP-random', 12, 36, 16384, 'step'),          # configs[3] shape (N scaled to --envs)
     'uc-random6': ('UC-random', 6, 24, 16384, 'step'),            # configs[4] shape, step kernel
     'uc-random6-replay': ('UC-random', 6, 24, 4096, 'replay'),    # configs[4]: replay kernel, T=64
+    'sp-random12-replay': ('SP-random', 12, 36, 4096, 'replay'),
+    'sp-ghz5-replay': ('SP-ghz5', 5, 20, 65536, 'replay'),
 }
 METRIC = "batched env-steps/sec"
 UNIT = "env-steps/s"
@@ -124,11 +126,12 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def make_tape(n_qubits: int, T: int, N: int, seed: int):
-  """[T,N,4] float32 actions ~ Box.sample() of env.py:46-49 (uniform in the float32 bounds)."""
+def make_tape(n_qubits: int, T: int, N: int, seed: int, no_terminate: bool = False):
+  """[T,N,4] float32 actions ~ Box.sample() of env.py:46-49 (uniform in the float32 bounds).
+  no_terminate: gate index drawn from [0,2) so that episodes run into the depth truncation."""
   m = 1e-5
   low = np.array([0, 0, 0, -np.pi]).astype(np.float32)
-  high = np.array([3 - m, n_qubits - m, n_qubits - m, np.pi]).astype(np.float32)
+  high = np.array([(2 if no_terminate else 3) - m, n_qubits - m, n_qubits - m, np.pi]).astype(np.float32)
   rng = np.random.default_rng(seed)
   return rng.uniform(low=low, high=high, size=(T, N, 4)).astype(np.float32)
 
@@ -273,7 +276,8 @@ def run_native(args):
   R = max(1, min(R, int(0.8 * free // per_replica)))
   batches = [probe] + [EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
                                 fused_stats=not args.no_stats, device=dev) for _ in range(R - 1)]
-  tape_np = make_tape(eta, TAPE_LEN if mode == 'step' else REPLAY_T * 2, N, seed=1234 + rank)
+  tape_np = make_tape(eta, TAPE_LEN if mode == 'step' else REPLAY_T * 2, N, seed=1234 + rank,
+                      no_terminate=args.no_terminate)
   tape = torch.as_tensor(tape_np, device=dev)
 
   if mode == 'step':
@@ -389,8 +393,10 @@ def run_native(args):
     except Exception:
       traffic = None
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-              "traffic": traffic, "peak_source": peak_src, "kernel": "qcd::qcd_kernel<%d,%s,%s>" % (
-                  int(np.log2(S)), "UC" if 'UC' in objective else "SP", "step" if mode == 'step' else "replay"),
+              "traffic": traffic, "peak_source": peak_src, "kernel": "qcd::%s<log2S=%d,%s>" % (
+                  ("step_warp_kernel" if S <= 256 else "qcd_kernel(pair-streaming step)") if mode == 'step' else
+                  ("replay_cta_kernel" if S >= 512 else "qcd_kernel(staged replay)"),
+                  int(np.log2(S)), "UC" if 'UC' in objective else "SP"),
               "algorithmic_bytes_per_env_step": bytes_step_env, "launch_us": launch_ms * 1e3}
 
   # ---- CPU baseline beside it (rank 0, one core, bounded sample)
@@ -407,8 +413,8 @@ def run_native(args):
       "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "complex128", "data": "synthetic",
       "config": {"workload": f"{objective} eta={eta} max_depth={delta} envs_per_gpu={N}", "mode": mode,
-                 "envs_total": N * world, "actions": "uniform-box float32 (Box.sample distribution), tape of "
-                 f"{TAPE_LEN} steps reused", "punish": True, "sparse": True, "autoreset": True,
+                 "envs_total": N * world, "actions": ("no-terminate" if args.no_terminate else "uniform-box") +
+                 " float32 (Box.sample distribution), tape of " f"{TAPE_LEN if mode == 'step' else 2 * REPLAY_T} steps reused", "punish": True, "sparse": True, "autoreset": True,
                  "observations": obs_mode, "final_obs": bool(args.final_obs), "fused_stats": not args.no_stats,
                  "l2": f"{R} batch replicas stepped round-robin, footprint {R * footprint / 1e6:.0f} MB > L2 "
                        f"126 MB" if R > 1 else "single batch (no rotation)",
@@ -435,6 +441,7 @@ def main():
   ap.add_argument("--final-obs", action="store_true", help="also write terminal observations of finished envs")
   ap.add_argument("--no-graph", action="store_true")
   ap.add_argument("--no-rotate", action="store_true", help="single batch replica (L2-resident at small sizes)")
+  ap.add_argument("--no-terminate", action="store_true", help="action tape without Terminate (episodes end by depth)")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--no-stats", action="store_true", help="do not accumulate episode statistics in the step kernel")
   ap.add_argument("--cpu-seconds", type=float, default=10.0)

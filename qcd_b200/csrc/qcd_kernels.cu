@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "qcd_b200.h"
 
@@ -47,6 +48,24 @@ namespace qcd {
 #endif
 #ifndef QCD_WARP_STEP_MINB
 #define QCD_WARP_STEP_MINB 16          // min CTAs per SM for __launch_bounds__ (caps registers at 128)
+#endif
+#ifndef QCD_REPLAY_WARP
+#define QCD_REPLAY_WARP 1               // replay for S <= 256: warp-autonomous, tile resident in smem
+#endif
+#ifndef QCD_WARP_REPLAY_WARPS
+#define QCD_WARP_REPLAY_WARPS 1
+#endif
+#ifndef QCD_WARP_REPLAY_MINB
+#define QCD_WARP_REPLAY_MINB 16
+#endif
+#ifndef QCD_WARP_REPLAY_TILE_BYTES
+#define QCD_WARP_REPLAY_TILE_BYTES 8192
+#endif
+#ifndef QCD_REPLAY_MINB
+#define QCD_REPLAY_MINB 3
+#endif
+#ifndef QCD_REPLAY_CTA
+#define QCD_REPLAY_CTA 1                // replay for S >= 512: CTA per env with decode-ahead (0: first version)
 #endif
 #ifndef QCD_WARP_UNROLL_CHUNKS
 #define QCD_WARP_UNROLL_CHUNKS 0
@@ -115,34 +134,40 @@ __device__ __forceinline__ void load_action(const void* __restrict__ actions, in
   }
 }
 
-// env.py:90-100 (decode) + QuantumCircuit.depth/count_ops/idle_wires bookkeeping (env.py:74,77,86)
-// + truncation (env.py:129) + cost (env.py:112).  Integer results are bit-exact by construction:
-// floor() is taken in float64 on exactly-widened inputs and the range test is done before the cast.
-__device__ __forceinline__ void decode_action(const qcd_batch_t& b, double a0, double a1, double a2,
-                                              double a3, EnvCtl& e, GateRec& rec) {
+// env.py:90-100: the part of the decode that depends on the action alone (parallel over steps in the
+// replay kernels).  Integer results are bit-exact by construction: floor() is taken in float64 on
+// exactly-widened inputs and the range test is done before the cast.
+struct GateKind { int status, kind, w, c; bool term; double cr, sr; };
+
+__device__ __forceinline__ GateKind decode_kind(const int n_qubits, double a0, double a1, double a2, double a3) {
   const double fg = floor(a0), fw = floor(a1), fc = floor(a2);
-  const double eta = (double)b.n_qubits;
-  int status = QCD_ST_OK;
-  if (!(fw >= 0.0 && fw < eta && fc >= 0.0 && fc < eta)) status = QCD_ST_BAD_WIRE;     // env.py:94
-  else if (!(fg == 0.0 || fg == 1.0 || fg == 2.0)) status = QCD_ST_BAD_GATE;           // env.py:100
-  int kind = K_NONE, w = 0, c = 0;
-  bool term = false;
-  if (status == QCD_ST_OK) {
-    w = (int)fw; c = (int)fc;
+  const double eta = (double)n_qubits;
+  GateKind k;
+  k.status = QCD_ST_OK; k.kind = K_NONE; k.w = 0; k.c = 0; k.term = false; k.cr = 1.0; k.sr = 0.0;
+  if (!(fw >= 0.0 && fw < eta && fc >= 0.0 && fc < eta)) k.status = QCD_ST_BAD_WIRE;     // env.py:94
+  else if (!(fg == 0.0 || fg == 1.0 || fg == 2.0)) k.status = QCD_ST_BAD_GATE;           // env.py:100
+  if (k.status == QCD_ST_OK) {
+    k.w = (int)fw; k.c = (int)fc;
     const int g = (int)fg;
-    if (g == 2) term = true;                                   // env.py:99 (checked after 95-98,
-    else if (w == c) kind = (g == 0) ? K_P : K_RX;             //  but g==2 matches none of those)
-    else kind = (g == 0) ? K_CP : K_CX;
+    if (g == 2) k.term = true;                                 // env.py:99 (checked after 95-98,
+    else if (k.w == k.c) k.kind = (g == 0) ? K_P : K_RX;       //  but g==2 matches none of those)
+    else k.kind = (g == 0) ? K_CP : K_CX;
   }
-  double cr = 1.0, sr = 0.0;
-  if (kind == K_P || kind == K_CP || kind == K_RX) {
-    const double arg = (kind == K_RX) ? a3 / 2 : a3;           // RXGate: cos/sin(theta/2)
+  if (k.kind == K_P || k.kind == K_CP || k.kind == K_RX) {
+    const double arg = (k.kind == K_RX) ? a3 / 2 : a3;         // RXGate: cos/sin(theta/2)
 #if defined(QCD_EXP_NOSINCOS)
-    cr = 1.0 - arg * arg * 0.5; sr = arg;     // EXPERIMENT ONLY (wrong numerics): decode-latency probe
+    k.cr = 1.0 - arg * arg * 0.5; k.sr = arg;   // EXPERIMENT ONLY (wrong numerics): decode-latency probe
 #else
-    sincos(arg, &sr, &cr);
+    sincos(arg, &k.sr, &k.cr);
 #endif
   }
+  return k;
+}
+
+// QuantumCircuit.depth/count_ops/idle_wires bookkeeping (env.py:74,77,86) + truncation (env.py:129)
+// + cost (env.py:112): the sequential part (integer only, apart from the cost division).
+__device__ __forceinline__ void book_gate(const qcd_batch_t& b, const int status, const int kind, const int w,
+                                          const int c, const bool term, EnvCtl& e) {
   uint32_t ops = e.meta.w & 0xffffu, used = e.meta.w >> 16;
   if (kind != K_NONE) {
     const uint32_t dw = get_byte(e.meta, w), dc = get_byte(e.meta, c);
@@ -162,9 +187,15 @@ __device__ __forceinline__ void decode_action(const qcd_batch_t& b, double a0, d
   e.trunc = (status == QCD_ST_OK) &&
             (depth >= b.max_depth || (int)ops >= b.max_depth * b.n_qubits * 2);        // env.py:129
   e.cost_raw = fmax(0.0, (double)depth - b.depth_free) / b.cost_denom;                 // env.py:112
-  rec.cr = cr; rec.sr = sr; rec.kind = kind;
+}
+
+__device__ __forceinline__ void decode_action(const qcd_batch_t& b, double a0, double a1, double a2,
+                                              double a3, EnvCtl& e, GateRec& rec) {
+  const GateKind k = decode_kind(b.n_qubits, a0, a1, a2, a3);
+  book_gate(b, k.status, k.kind, k.w, k.c, k.term, e);
+  rec.cr = k.cr; rec.sr = k.sr; rec.kind = k.kind;
   const int shift = (b.objective == QCD_OBJ_UC) ? b.n_qubits : 0;   // UC: gate acts on the row index
-  rec.wbit = w + shift; rec.cbit = c + shift;
+  rec.wbit = k.w + shift; rec.cbit = k.c + shift;
   rec.flags = ((e.term || e.trunc) && (b.flags & QCD_F_AUTORESET)) ? RF_RESET : 0;
 }
 
@@ -628,6 +659,186 @@ step_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2 for large states (S >= 512): one CTA per env, the state resident in shared memory for the whole
+// tape.  What made the first replay kernel slow was a per-step serial chain (one thread decoding an
+// action with a double-precision sincos while 255 waited, two CTA barriers per step).  Here
+//   * the part of the decode that depends on the action alone (floor, range checks, gate kind, sincos)
+//     is done for NT steps at once, one step per thread, into a table in smem (tape is known ahead);
+//   * the sequential bookkeeping (depth stack, ops, wires, truncation, auto-reset) is integer work and
+//     is replicated in EVERY thread, so nobody waits for a broadcast;
+//   * one CTA barrier per step (the butterflies of step t+1 read amplitudes other threads wrote in
+//     step t); the metric partial sums ride on that barrier (double-buffered by step parity) and are
+//     only computed on steps where the metric is needed (every step if dense / recorded, else done|last);
+//   * diagonal gates touch only the amplitudes they change (P: half, CP: a quarter), CX only swaps.
+struct __align__(16) StepRec { double cr, sr; int pk; int pad; };
+
+template <int LOG2S, bool UC, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32, const int T,
+                  const qcd_tape_out_t out, const int metric_every_step) {
+  constexpr int S = 1 << LOG2S, PPT = (S / 2) / NT, U = PPT < 4 ? PPT : 4;
+  static_assert(PPT >= 1, "replay_cta_kernel: at least one pair per thread");
+  extern __shared__ __align__(16) double2 s_state[];          // [S]
+  __shared__ StepRec s_tab[NT];
+  __shared__ double2 s_wred[2][NT / 32];
+
+  const int tid = threadIdx.x;
+  const long env = blockIdx.x;
+  const long N = b.n_envs;
+  const bool autoreset = b.flags & QCD_F_AUTORESET;
+  const int shift = UC ? b.n_qubits : 0;
+  double2* gstate = reinterpret_cast<double2*>(b.state) + env * S;
+  const double2* tgt = reinterpret_cast<const double2*>(b.target) + ((b.flags & QCD_F_TARGET_PER_ENV) ? env * S : 0);
+
+#pragma unroll 4
+  for (int i = tid; i < S; i += NT) s_state[i] = gstate[i];
+
+  EnvCtl e;
+  e.meta = reinterpret_cast<const uint4*>(b.meta)[env];      // every thread keeps the bookkeeping
+  e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
+  if (tid == 0) {
+    if (b.last) { const double2 l2 = reinterpret_cast<const double2*>(b.last)[env]; e.last_m = l2.x; e.last_c = l2.y; }
+    if (b.ep_return) { e.ep_ret = b.ep_return[env]; e.ep_len = b.ep_length[env]; }
+  }
+  double* stats = stats_slice(b, env);
+  int par = 0;
+
+  for (int t0 = 0; t0 < T; t0 += NT) {
+    // ---- decode-ahead: step t0 + tid
+    if (t0 + tid < T) {
+      double a0, a1, a2, a3;
+      load_action(actions, act_f32, (long)(t0 + tid) * N + env, a0, a1, a2, a3);
+      const GateKind k = decode_kind(b.n_qubits, a0, a1, a2, a3);
+      StepRec r;
+      r.cr = k.cr; r.sr = k.sr; r.pad = 0;
+      r.pk = k.kind | (k.w << 3) | (k.c << 7) | (k.status << 11) | ((k.term ? 1 : 0) << 13);
+      s_tab[tid] = r;
+    }
+    __syncthreads();                                          // table (and, first time, the state) ready
+    const int nsteps = (T - t0) < NT ? (T - t0) : NT;
+#pragma unroll 1
+    for (int si = 0; si < nsteps; ++si) {
+      const int t = t0 + si;
+      const StepRec r = s_tab[si];
+      const int kind = r.pk & 7, w = (r.pk >> 3) & 15, c = (r.pk >> 7) & 15, status = (r.pk >> 11) & 3;
+      const bool term = (r.pk >> 13) & 1;
+      book_gate(b, status, kind, w, c, term, e);              // identical in every thread
+      const bool done = (status == QCD_ST_OK) && (e.term || e.trunc);
+      const bool reset = done && autoreset;
+      const bool want_metric = metric_every_step || done || t == T - 1;
+      GateRec g;
+      g.cr = r.cr; g.sr = r.sr; g.kind = kind; g.wbit = w + shift; g.cbit = c + shift; g.flags = 0;
+      const unsigned lowmask = (1u << g.wbit) - 1u;
+      const int wb = 1 << g.wbit;
+      double ra = 0.0, rb = 0.0;
+      if (want_metric) {
+#pragma unroll 1
+        for (int j0 = 0; j0 < PPT; j0 += U) {
+          int i0[U];
+          double2 x0[U], x1[U], t0v[U], t1v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const unsigned k = (unsigned)(tid + NT * (j0 + u));
+            i0[u] = (int)(((k & ~lowmask) << 1) | (k & lowmask));
+            x0[u] = s_state[i0[u]]; x1[u] = s_state[i0[u] | wb];
+            t0v[u] = __ldg(tgt + i0[u]); t1v[u] = __ldg(tgt + (i0[u] | wb));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            apply_pair(g, i0[u], x0[u], x1[u]);
+            metric_acc<UC>(x0[u], t0v[u], ra, rb);
+            metric_acc<UC>(x1[u], t1v[u], ra, rb);
+            if (reset) { x0[u] = reset_amp(UC, b.n_qubits, i0[u]); x1[u] = reset_amp(UC, b.n_qubits, i0[u] | wb); }
+            if (kind != K_NONE || reset) { s_state[i0[u]] = x0[u]; s_state[i0[u] | wb] = x1[u]; }
+          }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          ra += __shfl_xor_sync(0xffffffffu, ra, off);
+          rb += __shfl_xor_sync(0xffffffffu, rb, off);
+        }
+        if ((tid & 31) == 0) s_wred[par][tid >> 5] = make_double2(ra, rb);
+      } else if (kind != K_NONE) {                            // light path: touch only what changes
+#pragma unroll 4
+        for (int j = 0; j < PPT; ++j) {
+          const unsigned k = (unsigned)(tid + NT * j);
+          const int i0 = (int)(((k & ~lowmask) << 1) | (k & lowmask));
+          const bool cset = (i0 >> g.cbit) & 1;
+          if (kind == K_RX) {
+            const double2 a0 = s_state[i0], a1 = s_state[i0 | wb];
+            s_state[i0] = rot_rx(a0, a1, g.cr, g.sr);
+            s_state[i0 | wb] = rot_rx(a1, a0, g.cr, g.sr);
+          } else if (kind == K_P || (kind == K_CP && cset)) {
+            s_state[i0 | wb] = mul_phase(s_state[i0 | wb], g.cr, g.sr);
+          } else if (kind == K_CX && cset) {
+            const double2 a0 = s_state[i0], a1 = s_state[i0 | wb];
+            s_state[i0] = a1; s_state[i0 | wb] = a0;
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {                                         // env.py:106-114,133-135 + Monitor + records
+        double xa = 0.0, xb = 0.0;
+        if (want_metric) {
+#pragma unroll
+          for (int wv = 0; wv < NT / 32; ++wv) { xa += s_wred[par][wv].x; xb += s_wred[par][wv].y; }
+        }
+        const StepOut o = finalize_step<UC>(b, e, xa, xb, want_metric);
+        if (out.reward) out.reward[(long)t * N + env] = o.reward;
+        if (out.metric) out.metric[(long)t * N + env] = o.metric;
+        if (out.cost) out.cost[(long)t * N + env] = o.cost;
+        if (out.depth) out.depth[(long)t * N + env] = e.depth;
+        if (out.terminated) out.terminated[(long)t * N + env] = e.term;
+        if (out.truncated) out.truncated[(long)t * N + env] = e.trunc;
+        if (out.status) out.status[(long)t * N + env] = (int8_t)e.status;
+        if (t == T - 1) {
+          b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
+          b.depth[env] = e.depth; b.operations[env] = e.ops; b.used_wires[env] = e.used_cnt;
+          b.terminated[env] = e.term; b.truncated[env] = e.trunc; b.status[env] = (int8_t)e.status;
+        }
+        if (stats) {
+          if (e.status != QCD_ST_OK) atomicAdd(stats + QCD_STAT_BAD_ACTIONS, 1.0);
+          else atomicAdd(stats + QCD_STAT_STEPS, 1.0);
+        }
+        if (done) {
+          if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
+          if (stats) {
+            atomicAdd(stats + QCD_STAT_EPISODES, 1.0);
+            if (b.ep_return) { atomicAdd(stats + QCD_STAT_SUM_R, e.ep_ret); atomicAdd(stats + QCD_STAT_SUM_L, (double)e.ep_len); }
+            atomicAdd(stats + QCD_STAT_SUM_D, (double)e.depth); atomicAdd(stats + QCD_STAT_SUM_O, (double)e.ops);
+            atomicAdd(stats + QCD_STAT_SUM_Q, (double)e.used_cnt);
+            atomicAdd(stats + QCD_STAT_SUM_M, o.metric); atomicAdd(stats + QCD_STAT_SUM_C, o.cost);
+            atomicAdd(stats + (e.trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE), 1.0);
+          }
+          if (autoreset) { e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0; }
+        }
+      }
+      if (reset) e.meta = make_uint4(0, 0, 0, 0);             // env.py:117-121, every thread's copy
+      par ^= 1;
+    }
+    __syncthreads();                                          // table may be overwritten by the next chunk
+  }
+
+  // ---- the state (and the observation of the last step) go back to HBM once
+  float* ob = b.obs ? b.obs + env * b.obs_stride : nullptr;
+#pragma unroll 4
+  for (int i = tid; i < S; i += NT) {
+    const double2 v = s_state[i];
+    gstate[i] = v;
+    if (ob) { ob[i] = (float)v.x; ob[S + i] = (float)v.y; }
+  }
+  if (tid == 0) {
+    reinterpret_cast<uint4*>(b.meta)[env] = e.meta;
+    if (b.last) reinterpret_cast<double2*>(b.last)[env] = make_double2(e.last_m, e.last_c);
+    if (b.ep_return) { b.ep_return[env] = e.ep_ret; b.ep_length[env] = e.ep_len; }
+  }
+}
+
+// ---- programmatic dependent launch (no-ops when the launch does not carry the attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA (cp.async.bulk) + mbarrier helpers: 1-D bulk copies of a warp's contiguous state tile
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -737,12 +948,6 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   double2* tstate = reinterpret_cast<double2*>(b.state) + env_base * S;
   const double2* tgt = reinterpret_cast<const double2*>(b.target);   // shared target (per-env targets
                                                                      // take the pair-streaming kernel)
-  if (STAGE) {                                    // the tile goes in flight first
-    if (lane == 0) {
-      mbar_init(mbar, 1);
-      bulk_load(stile, tstate, (uint32_t)(n_valid * S * sizeof(double2)), mbar);
-    }
-  }
 
   // ---- scalar loads of env_base + lane (and, !STAGE, the state of the first PF rounds)
   const long env = env_base + lane;
@@ -750,8 +955,22 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   EnvCtl e;
   e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
+  // Programmatic dependent launch: this grid may have been started while the previous kernel of the
+  // stream (the previous env step) was still draining.  The action and its trig do not depend on
+  // that kernel; everything it wrote (meta, states, accumulators) is only touched after the wait.
+  GateKind gk;
   if (ctl) {
     load_action(actions, act_f32, env, a0, a1, a2, a3);
+    gk = decode_kind(b.n_qubits, a0, a1, a2, a3);
+  }
+  pdl_wait();
+  if (STAGE) {                                    // the tile goes in flight first
+    if (lane == 0) {
+      mbar_init(mbar, 1);
+      bulk_load(stile, tstate, (uint32_t)(n_valid * S * sizeof(double2)), mbar);
+    }
+  }
+  if (ctl) {
     e.meta = reinterpret_cast<const uint4*>(b.meta)[env];
     if (b.last) { const double2 l2 = reinterpret_cast<const double2*>(b.last)[env]; e.last_m = l2.x; e.last_c = l2.y; }
     if (b.ep_return) { e.ep_ret = b.ep_return[env]; e.ep_len = b.ep_length[env]; }
@@ -786,7 +1005,11 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
     double2 cs = make_double2(1.0, 0.0);
     if (ctl) {
       GateRec rec;
-      decode_action(b, a0, a1, a2, a3, e, rec);
+      book_gate(b, gk.status, gk.kind, gk.w, gk.c, gk.term, e);
+      rec.cr = gk.cr; rec.sr = gk.sr; rec.kind = gk.kind;
+      const int shift = UC ? b.n_qubits : 0;      // UC: gate acts on the row index
+      rec.wbit = gk.w + shift; rec.cbit = gk.c + shift;
+      rec.flags = ((e.term || e.trunc) && (b.flags & QCD_F_AUTORESET)) ? RF_RESET : 0;
       pk = pack_gate<LOG2L>(rec);
       cs = make_double2(rec.cr, rec.sr);
     }
@@ -934,6 +1157,7 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   }
 
   // ---- finalize + scalar outputs + fused statistics
+  pdl_launch_dependents();                        // the next step's grid may start its scalar phase now
   const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   phase3<UC, 32>(b, none, e, ctl, env, 0, 1, N, lane, mysum, ctl, stats_slice(b, tile));
   if (ctl) {
@@ -942,6 +1166,197 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
     if (b.ep_return) { b.ep_return[env] = e.ep_ret; b.ep_length[env] = e.ep_len; }
   }
   if (STAGE && lane == 0) bulk_store_wait_read(); // smem must outlive the bulk store's reads
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 for small states (S <= 256): the warp-autonomous scheme with the tile RESIDENT in shared memory
+// for the whole tape.  One cp.async.bulk brings the warp's TE states in, T times {lane-per-env decode,
+// rounds in place in smem, transposed metric reduction, finalize + per-step records}, one bulk store
+// writes the tile back, observations are produced once from the final states.  The next step's action
+// is prefetched while the current step runs.  Same arithmetic as the step kernel (bit-identical states).
+template <int LOG2S, bool UC, int WARPS, int TE, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+replay_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32, const int T,
+                   const qcd_tape_out_t out, const int metric_every_step) {
+  using W = WarpCfg<LOG2S, TE, true>;
+  constexpr int S = W::S, LOG2L = W::LOG2L, L = W::L, V = W::V, LOG2V = W::LOG2V, G = W::G, LOG2G = W::LOG2G;
+  constexpr int R = W::R, C = W::C, ROW = W::ROW, SUMS = W::SUMS, P = W::P, VAL = W::VAL;
+  constexpr unsigned FULL = 0xffffffffu;
+  (void)metric_every_step;                        // the metric of every step is cheap here: always computed
+
+  extern __shared__ __align__(128) double2 s_dyn[];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long tile = (long)blockIdx.x * WARPS + warp;
+  const long N = b.n_envs;
+  const long env_base = tile * TE;
+  if (env_base >= N) return;
+  const int n_valid = (int)((N - env_base) < TE ? (N - env_base) : TE);
+  const int li = lane & (L - 1), gi = lane >> LOG2L;
+  double2* wsm = s_dyn + (long)warp * W::WARP_SLOTS;
+  double2* stile = wsm;
+  double2* part = wsm + W::TILE;
+  double2* s_cs = part + C * ROW;
+  int* s_pk = reinterpret_cast<int*>(s_cs + 32);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_cs + 32 + 8);
+  double2* tstate = reinterpret_cast<double2*>(b.state) + env_base * S;
+  const double2* tgt = reinterpret_cast<const double2*>(b.target);
+
+  if (lane == 0) {
+    mbar_init(mbar, 1);
+    bulk_load(stile, tstate, (uint32_t)(n_valid * S * sizeof(double2)), mbar);
+  }
+
+  const long env = env_base + lane;
+  const bool ctl = lane < TE && env < N;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  EnvCtl e;
+  e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
+  if (ctl) {
+    load_action(actions, act_f32, env, a0, a1, a2, a3);
+    e.meta = reinterpret_cast<const uint4*>(b.meta)[env];
+    if (b.last) { const double2 l2 = reinterpret_cast<const double2*>(b.last)[env]; e.last_m = l2.x; e.last_c = l2.y; }
+    if (b.ep_return) { e.ep_ret = b.ep_return[env]; e.ep_len = b.ep_length[env]; }
+  }
+  double2* stp = stile + gi * S + li;
+  double2 tv[V];
+  double rv[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    tv[j] = __ldg(tgt + li + L * j);
+    rv[j] = reset_amp(UC, b.n_qubits, li + L * j).x;
+  }
+  double* stats = stats_slice(b, tile);
+
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    // ---- scalar phase of step t; the action of step t+1 goes in flight
+    {
+      int pk = 0;
+      double2 cs = make_double2(1.0, 0.0);
+      if (ctl) {
+        GateRec rec;
+        decode_action(b, a0, a1, a2, a3, e, rec);
+        pk = pack_gate<LOG2L>(rec);
+        cs = make_double2(rec.cr, rec.sr);
+        if (t + 1 < T) load_action(actions, act_f32, (long)(t + 1) * N + env, a0, a1, a2, a3);
+      }
+      s_cs[lane] = cs; s_pk[lane] = pk;
+    }
+    __syncwarp();
+    if (t == 0) mbar_wait(mbar, 0);
+
+    double2 mysum = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < R; c0 += C) {
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const int src = (c0 + k) * G + gi;
+        const double2 cs = s_cs[src];
+        const int pk = s_pk[src];
+        const int kind = pk & 7;
+        const bool reset = pk & 8;
+        const unsigned wm = (pk >> 11) & 0xffu, cm = (pk >> 19) & 0xffu;
+        const bool act = src < n_valid;
+        double2* sp = stp + (c0 + k) * G * S;
+        double2 cur[V], pv[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) cur[j] = act ? sp[L * j] : make_double2(0.0, 0.0);
+        const bool need_p = kind == K_RX || kind == K_CX;
+        if (__any_sync(FULL, need_p)) {
+          const int src_lane = lane ^ ((pk >> 4) & 31);
+          const int jsel = (pk >> 9) & 3;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            double2 p = cur[j];
+            if (LOG2V > 0) {
+#pragma unroll
+              for (int bit = 0; bit < LOG2V; ++bit) {
+                const double2 cand = cur[j ^ (1 << bit)];
+                const bool take = jsel == bit + 1;
+                p.x = take ? cand.x : p.x; p.y = take ? cand.y : p.y;
+              }
+            }
+            pv[j].x = __shfl_sync(FULL, p.x, src_lane);
+            pv[j].y = __shfl_sync(FULL, p.y, src_lane);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < V; ++j) pv[j] = cur[j];
+        }
+        double ra, rb;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const unsigned i = li + L * j;
+          const bool bw = i & wm, bc = i & cm;
+          double2 v = cur[j];
+          switch (kind) {
+            case K_P:  if (bw) v = mul_phase(v, cs.x, cs.y); break;
+            case K_CP: if (bw && bc) v = mul_phase(v, cs.x, cs.y); break;
+            case K_RX: v = rot_rx(v, pv[j], cs.x, cs.y); break;
+            case K_CX: if (bc) v = pv[j]; break;
+            default: break;
+          }
+          if (j == 0) metric_set<UC>(v, tv[j], ra, rb); else metric_acc<UC>(v, tv[j], ra, rb);
+          if (act) {
+            if (reset) sp[L * j] = make_double2(rv[j], 0.0);
+            else if (kind != K_NONE) sp[L * j] = v;
+          }
+        }
+        part[k * ROW + lane] = make_double2(ra, rb);
+      }
+      __syncwarp();
+      {
+        const int sidx = lane / P, prt = lane % P;
+        const int k = sidx >> LOG2G, g2 = sidx & (G - 1);
+        const double2* row = part + k * ROW + g2 * L + prt;
+        double xa = 0.0, xb = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < VAL; ++jj) {
+          const double2 q = row[P * ((jj + g2) & (VAL - 1))];
+          xa += q.x; xb += q.y;
+        }
+#pragma unroll
+        for (int off = P / 2; off >= 1; off >>= 1) {
+          xa += __shfl_xor_sync(FULL, xa, off);
+          xb += __shfl_xor_sync(FULL, xb, off);
+        }
+        const int want = lane - c0 * G;
+        const int from = (want & (SUMS - 1)) * P;
+        const double va = __shfl_sync(FULL, xa, from), vb = __shfl_sync(FULL, xb, from);
+        if (want >= 0 && want < SUMS) mysum = make_double2(va, vb);
+      }
+      __syncwarp();
+    }
+    phase3<UC, 32>(b, out, e, ctl, env, t, T, N, lane, mysum, ctl, stats);
+    __syncwarp();                                 // s_cs / s_pk are rewritten by the next step
+  }
+
+  if (ctl) {
+    reinterpret_cast<uint4*>(b.meta)[env] = e.meta;
+    if (b.last) reinterpret_cast<double2*>(b.last)[env] = make_double2(e.last_m, e.last_c);
+    if (b.ep_return) { b.ep_return[env] = e.ep_ret; b.ep_length[env] = e.ep_len; }
+  }
+  if (b.obs) {                                    // observation of the final states (env.py:85)
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+      const int src = r * G + gi;
+      if (src < n_valid) {
+        float* o = b.obs + (env_base + src) * b.obs_stride + li;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const double2 v = stp[r * G * S + L * j];
+          o[L * j] = (float)v.x; o[S + L * j] = (float)v.y;
+        }
+      }
+    }
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_store(tstate, stile, (uint32_t)(n_valid * S * sizeof(double2)));
+    bulk_store_wait_read();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1016,6 +1431,11 @@ stats_kernel(const qcd_batch_t b, double* __restrict__ stats) {
 
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
+static bool pdl_enabled() {     // QCD_PDL=0 in the environment turns programmatic dependent launch off
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("QCD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 
@@ -1032,7 +1452,43 @@ struct Launch {
 
   static int run(const qcd_batch_t& b, const void* actions, int act_f32, int T,
                  const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream) {
-    if constexpr (REG && QCD_STEP_IMPL == 2) {
+    if constexpr (STAGED && S >= 512 && QCD_REPLAY_CTA) {
+      constexpr int RNT = (S / 2) < 256 ? (S / 2) : 256;
+      constexpr size_t smem = (size_t)S * sizeof(double2);
+      constexpr int MINB = S >= 4096 ? QCD_REPLAY_MINB : (S >= 2048 ? 4 : 6);   // smem allows 3 CTAs of 64 KiB
+      auto kern = replay_cta_kernel<LOG2S, UC, RNT, MINB>;
+      static bool attr_done[64] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (smem > 40 * 1024 && !attr_done[dev & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        attr_done[dev & 63] = true;
+      }
+      kern<<<(unsigned)b.n_envs, RNT, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
+      return (int)cudaGetLastError();
+    } else if constexpr (STAGED && S <= 256 && QCD_REPLAY_WARP) {
+      if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
+      constexpr int W = QCD_WARP_REPLAY_WARPS;
+      constexpr int G = S < 32 ? 32 / S : 1;
+      constexpr int TE0 = clampi(QCD_WARP_REPLAY_TILE_BYTES / (S * 16), 1, 32);
+      constexpr int TE = TE0 < G ? G : TE0;
+      using WC = WarpCfg<LOG2S, TE, true>;
+      constexpr size_t smem = (size_t)W * WC::WARP_SLOTS * sizeof(double2);
+      auto kern = replay_warp_kernel<LOG2S, UC, W, TE, QCD_WARP_REPLAY_MINB>;
+      static bool attr_done[64] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (smem > 48 * 1024 && !attr_done[dev & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        attr_done[dev & 63] = true;
+      }
+      const long tiles = ((long)b.n_envs + TE - 1) / TE;
+      const unsigned grid = (unsigned)((tiles + W - 1) / W);
+      kern<<<grid, W * 32, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
+      return (int)cudaGetLastError();
+    } else if constexpr (REG && QCD_STEP_IMPL == 2) {
       if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
       constexpr int W = QCD_WARP_STEP_WARPS;
       constexpr int G = S < 32 ? 32 / S : 1;
@@ -1052,8 +1508,13 @@ struct Launch {
       }
       const long tiles = ((long)b.n_envs + TE - 1) / TE;
       const unsigned grid = (unsigned)((tiles + W - 1) / W);
-      kern<<<grid, W * 32, smem, stream>>>(b, actions, act_f32);
-      return (int)cudaGetLastError();
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(W * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+      return (int)cudaLaunchKernelEx(&cfg, kern, b, actions, act_f32);
     } else if constexpr (REG && QCD_STEP_IMPL == 1) {
       constexpr int RNT = QCD_REG_STEP_THREADS;
       constexpr int RL = clampi(S / 4, 1, 32);                // V = 4 amplitudes per lane (8 at S=256)
