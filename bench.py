@@ -346,6 +346,38 @@ def run_native(args):
   env_steps = N * K * steps_per_launch * world
   value = env_steps / (elapsed_ms * 1e-3)
 
+  # ---- secondary point: the same kernel at 1 Mi envs per GPU (steady state, launch ramp amortised)
+  sweep = None
+  if mode == 'step' and not args.no_sweep and args.envs == 0 and S <= 64:
+    del batches, probe
+    torch.cuda.empty_cache()
+    Nb = 1 << 20
+    big = [EnvBatch(Nb, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
+                    fused_stats=not args.no_stats, device=dev) for _ in range(2)]
+    tape_b = torch.as_tensor(make_tape(eta, 4, Nb, seed=99 + rank, no_terminate=args.no_terminate), device=dev)
+    Kb = 120
+    with torch.cuda.stream(stream):
+      for i in range(8):
+        big[i % 2].step(tape_b[i % 4])
+      stream.synchronize()
+      if world > 1:
+        dist.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(stream)
+      for i in range(Kb):
+        big[i % 2].step(tape_b[i % 4])
+      e1.record(stream)
+      stream.synchronize()
+    tb = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    ms_b = float(tb.item()) / Kb
+    sweep = {"envs_per_gpu": Nb, "steps": Kb, "ms_per_step": ms_b, "value": Nb * world / (ms_b * 1e-3),
+             "roofline_frac": bytes_step_env * Nb / (ms_b * 1e-3) / 1e9 / load_peaks()[0],
+             "l2": "2 batch replicas alternated, 1.8 GB footprint"}
+    del big, tape_b
+    torch.cuda.empty_cache()
+
   # ---- end to end through the public API with HOST buffers (step workloads only)
   e2e = None
   if mode == 'step':
@@ -421,7 +453,7 @@ def run_native(args):
                  "cuda_graph": graph is not None, "graph_len": G if graph is not None else 0,
                  "steps_per_launch": steps_per_launch, "parallelism": f"env-sharded x{world}, stats all-reduce only"},
       "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu,
-      "episode_stats": summarize(stats),
+      "episode_stats": summarize(stats), "sweep": sweep,
   }
   print(json.dumps(line), flush=True)
   if world > 1:
@@ -442,6 +474,7 @@ def main():
   ap.add_argument("--no-graph", action="store_true")
   ap.add_argument("--no-rotate", action="store_true", help="single batch replica (L2-resident at small sizes)")
   ap.add_argument("--no-terminate", action="store_true", help="action tape without Terminate (episodes end by depth)")
+  ap.add_argument("--no-sweep", action="store_true", help="skip the secondary 1 Mi-env measurement")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--no-stats", action="store_true", help="do not accumulate episode statistics in the step kernel")
   ap.add_argument("--cpu-seconds", type=float, default=10.0)

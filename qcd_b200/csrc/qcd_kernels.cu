@@ -49,6 +49,9 @@ namespace qcd {
 #ifndef QCD_WARP_STEP_MINB
 #define QCD_WARP_STEP_MINB 16          // min CTAs per SM for __launch_bounds__ (caps registers at 128)
 #endif
+#ifndef QCD_PDL_EARLY
+#define QCD_PDL_EARLY 0
+#endif
 #ifndef QCD_REPLAY_WARP
 #define QCD_REPLAY_WARP 1               // replay for S <= 256: warp-autonomous, tile resident in smem
 #endif
@@ -483,7 +486,16 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
             x0[u] = reset_amp(UC, b.n_qubits, i0[u]);
             x1[u] = reset_amp(UC, b.n_qubits, i1);
           }
-          if (wr_state) { st[i0[u]] = x0[u]; st[i1] = x1[u]; }
+          if (wr_state) {
+            // store only what the gate changed: P/CP leave a0 (and a1 without the control bit)
+            // untouched, CX only swaps pairs whose control bit is set.  Whole 32-byte sectors stay
+            // clean for every wire bit >= 1.
+            const bool cset = (i0[u] >> g.cbit) & 1;
+            const bool ch1 = STAGED || reset || g.kind == K_RX || g.kind == K_P || ((g.kind == K_CP || g.kind == K_CX) && cset);
+            const bool ch0 = STAGED || reset || g.kind == K_RX || (g.kind == K_CX && cset);
+            if (ch0) st[i0[u]] = x0[u];
+            if (ch1) st[i1] = x1[u];
+          }
           if (ob) {
             ob[i0[u]] = (float)x0[u].x; ob[S + i0[u]] = (float)x0[u].y;
             ob[i1] = (float)x1[u].x;    ob[S + i1] = (float)x1[u].y;
@@ -963,6 +975,9 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
     load_action(actions, act_f32, env, a0, a1, a2, a3);
     gk = decode_kind(b.n_qubits, a0, a1, a2, a3);
   }
+#if QCD_PDL_EARLY
+  pdl_launch_dependents();                        // the next step's grid may start its scalar phase now
+#endif
   pdl_wait();
   if (STAGE) {                                    // the tile goes in flight first
     if (lane == 0) {
@@ -1115,7 +1130,12 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-              if (kind != K_NONE) { if (STAGE) stile[src * S + li + L * j] = y[j]; else sp[k * G * S + L * j] = y[j]; }
+              // store only amplitudes the gate changed (whole sectors stay clean for wire bits >= 1)
+              const unsigned i = li + L * j;
+              const bool bw = i & wm, bc = i & cm;
+              const bool changed = STAGE ? (kind != K_NONE)
+                                         : (kind == K_RX || (kind == K_P && bw) || (kind == K_CP && bw && bc) || (kind == K_CX && bc));
+              if (changed) { if (STAGE) stile[src * S + li + L * j] = y[j]; else sp[k * G * S + L * j] = y[j]; }
               if (op) { op[L * j] = (float)y[j].x; op[S + L * j] = (float)y[j].y; }
             }
           }
@@ -1157,7 +1177,9 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   }
 
   // ---- finalize + scalar outputs + fused statistics
+#if !QCD_PDL_EARLY
   pdl_launch_dependents();                        // the next step's grid may start its scalar phase now
+#endif
   const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   phase3<UC, 32>(b, none, e, ctl, env, 0, 1, N, lane, mysum, ctl, stats_slice(b, tile));
   if (ctl) {
