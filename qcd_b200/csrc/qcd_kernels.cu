@@ -38,7 +38,7 @@
 namespace qcd {
 
 #ifndef QCD_REG_STEP_MAX_LOG2S
-#define QCD_REG_STEP_MAX_LOG2S 8     // S <= 256: register-resident step kernel
+#define QCD_REG_STEP_MAX_LOG2S 7     // S <= 128: warp-autonomous step kernel; above: pair-streaming
 #endif
 #ifndef QCD_STEP_IMPL
 #define QCD_STEP_IMPL 2                // small-S step path: 0 pair-streaming, 1 CTA register-resident, 2 warp-autonomous
@@ -48,6 +48,18 @@ namespace qcd {
 #endif
 #ifndef QCD_WARP_STEP_MINB
 #define QCD_WARP_STEP_MINB 16          // min CTAs per SM for __launch_bounds__ (caps registers at 128)
+#endif
+#ifndef QCD_PAIR_SMALL_MAX_S
+#define QCD_PAIR_SMALL_MAX_S 4096
+#endif
+#ifndef QCD_PAIR_SMALL_THREADS
+#define QCD_PAIR_SMALL_THREADS 32    // pair-streaming step: one warp (= one env) per CTA measured best at every S
+#endif
+#ifndef QCD_PAIR_L2_PREFETCH
+#define QCD_PAIR_L2_PREFETCH 1
+#endif
+#ifndef QCD_PAIR_L2_PREFETCH_MAX_S
+#define QCD_PAIR_L2_PREFETCH_MAX_S 1024
 #endif
 #ifndef QCD_PDL_EARLY
 #define QCD_PDL_EARLY 0
@@ -421,6 +433,16 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
     if (b.ep_return) { e.ep_ret = b.ep_return[cenv]; e.ep_len = b.ep_length[cenv]; }
   }
 
+  if (!STAGED && QCD_PAIR_L2_PREFETCH && S <= QCD_PAIR_L2_PREFETCH_MAX_S) {
+    // The pair addresses depend on the decoded wire, so the state loads cannot be issued before the
+    // barrier below; pull the env's lines into L2 meanwhile (128-byte lines, L lanes per env).
+    if (gact) {
+      const char* base = reinterpret_cast<const char*>(gstate + genv * S);
+#pragma unroll 1
+      for (int ln = lane; ln < S * 16 / 128; ln += L)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long)ln * 128));
+    }
+  }
   if (STAGED) {                                   // stage the CTA's contiguous block of states
     const long base = env0 * S;
     const long lim = (N - env0 < E ? N - env0 : E) * (long)S;
@@ -1465,7 +1487,7 @@ template <int LOG2S, bool UC, bool STAGED>
 struct Launch {
   static constexpr int S = 1 << LOG2S;
   // step: <= one warp per env, streaming.  replay: a whole CTA per env once the state is >= 32 KiB.
-  static constexpr int NT = STAGED ? (S >= 2048 ? 256 : 128) : 256;
+  static constexpr int NT = STAGED ? (S >= 2048 ? 256 : 128) : (S <= QCD_PAIR_SMALL_MAX_S ? QCD_PAIR_SMALL_THREADS : 256);
   static constexpr int L = (STAGED && S >= 2048) ? NT : clampi(S / 4, 1, 32);
   static constexpr int LOG2L = ilog2(L);
   static constexpr int E = NT / L;

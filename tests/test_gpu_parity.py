@@ -161,3 +161,33 @@ def test_stats_reduction(cuda_device, fused):
              (fin & ~ora.truncated.astype(bool)).sum(), ora.truncated.sum(), N, 0]
   np.testing.assert_allclose(gpu.stats.cpu().numpy(), want, rtol=1e-12)
   np.testing.assert_allclose(ora.stats, want, rtol=1e-12)
+
+
+def test_large_batch_indexing(cuda_device):
+  """> 4 GiB of state: 2^30 amplitudes (262 144 envs x eta=12).  Env i replays the tape of env
+  i mod 256, so every block of 256 envs must be bit-identical to the first one, which is checked
+  against the oracle.  Guards the 64-bit index arithmetic of the step / reset kernels."""
+  from qcd_b200.batch import EnvBatch
+  free, _ = torch.cuda.mem_get_info(cuda_device)
+  N, eta, delta, M, T = 262144, 12, 36, 256, 6
+  if free < 45e9:
+    pytest.skip("needs ~35 GB of device memory")
+  rng = np.random.default_rng(11)
+  target = make_target('SP-random', eta, seed=1)
+  small = uniform_box_tape(rng, eta, T, M)
+  gpu = EnvBatch(N, eta, delta, 'SP-random', target, obs_mode='state')
+  ora = OracleBatch(M, eta, delta, 'SP-random', target, obs_mode='state')
+  for t in range(T):
+    a = torch.as_tensor(small[t], device=cuda_device).repeat(N // M, 1)
+    gpu.step(a); ora.step(small[t])
+  st = gpu.state.view(N // M, M, -1)
+  assert torch.equal(st, st[:1].expand_as(st))
+  ob = gpu.obs.view(N // M, M, -1)
+  assert torch.equal(ob, ob[:1].expand_as(ob))
+  for name in ('reward', 'depth', 'terminated', 'truncated'):
+    v = getattr(gpu, name).view(N // M, M)
+    assert torch.equal(v, v[:1].expand_as(v)), name
+  np.testing.assert_allclose(gpu.state[-M:].cpu().numpy(), ora.state, atol=TOL, rtol=0)
+  np.testing.assert_allclose(gpu.reward[-M:].cpu().numpy(), ora.reward, atol=TOL, rtol=0)
+  np.testing.assert_array_equal(gpu.depth[-M:].cpu().numpy(), ora.depth)
+  assert gpu.stats[10].item() == N * T
