@@ -1,0 +1,86 @@
+"""Device-side drivers of the two non-RL baselines that call the hot path.
+
+random_baseline : /root/reference/plot/metrics.py:161-176 — per seed, 100 episodes of
+                  `env.step(env.action_space.sample())`, mean of the Monitor fields r,d,q,m,c.
+circuit_fitness : /root/reference/baselines/evo/run.py:17-33 — fitness of whole circuits of
+                  cx/rx/cp/p gates: fidelity | similarity minus the depth cost, evaluated with the
+                  replay kernel (one launch for the whole population).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batch import EnvBatch
+from .targets import make_target, parse_task
+from .vector_env import action_space_for
+
+
+def sample_actions(n: int, qubits: int, generator: torch.Generator, device) -> torch.Tensor:
+  """[n,4] float32 ~ Box.sample(): uniform in the float32 bounds of env.py:46-49, on the device."""
+  sp = action_space_for(qubits)
+  low = torch.as_tensor(sp.low, device=device, dtype=torch.float64)
+  high = torch.as_tensor(sp.high, device=device, dtype=torch.float64)
+  u = torch.rand((n, 4), generator=generator, device=device, dtype=torch.float64)
+  return (low + (high - low) * u).to(torch.float32).clamp_(sp.low.min().item(), None)
+
+
+def random_baseline(task: str, seeds: int = 8, episodes: int = 100, env_seed: int = 42, device=None) -> dict:
+  """Means of Return/Depth/Qubits/Metric/Cost per seed for `task` = '<obj>-q<eta>-d<delta>'.
+
+  Every (seed, episode) pair is its own env: seeds*episodes envs are stepped in lock-step with
+  auto-reset off until all have finished (episodes are independent, so this is the same experiment as
+  the reference's sequential loop; the action streams differ from numpy's, the distribution does not)."""
+  kw = parse_task(task)
+  eta, delta, objective = kw['max_qubits'], kw['max_depth'], kw['objective']
+  dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+  n = seeds * episodes
+  batch = EnvBatch(n, eta, delta, objective, make_target(objective, eta, env_seed), autoreset=False, obs_mode='none',
+                   track_episodes=True, fused_stats=False, device=dev)
+  gens = [torch.Generator(device=dev).manual_seed(s + 1) for s in range(seeds)]
+  done = torch.zeros(n, dtype=torch.bool, device=dev)
+  out = {k: torch.zeros(n, dtype=torch.float64, device=dev) for k in 'rdqmc'}
+  for _ in range(delta * eta * 2 + 1):                       # env.py:37 max_steps bounds an episode
+    actions = torch.cat([sample_actions(episodes, eta, g, dev) for g in gens])
+    batch.step(actions)
+    fin = (batch.terminated.bool() | batch.truncated.bool()) & ~done
+    for k, src in zip('rdqmc', (batch.episode_return, batch.depth, batch.used_wires, batch.metric, batch.cost)):
+      out[k] = torch.where(fin, src.to(torch.float64), out[k])
+    done |= fin
+    if bool(done.all()):
+      break
+  names = {'r': 'Return', 'd': 'Depth', 'q': 'Qubits', 'm': 'Metric', 'c': 'Cost'}
+  return {names[k]: v.view(seeds, episodes).mean(1).cpu().numpy() for k, v in out.items()}
+
+
+GATE_CODES = {'p': 0, 'cp': 0, 'rx': 1, 'cx': 1}              # env.py:95-98: gate index of each kind
+
+
+def encode_circuit(gates, max_len: int) -> np.ndarray:
+  """[(kind, wire, control, theta)] -> [max_len+1, 4] float64 actions, padded with Terminate (gate 2)."""
+  tape = np.zeros((max_len + 1, 4), np.float64)
+  tape[:, 0] = 2
+  for t, (kind, wire, cntrl, theta) in enumerate(gates):
+    single = kind in ('p', 'rx')
+    tape[t] = (GATE_CODES[kind], wire, wire if single else cntrl, 0.0 if theta is None else theta)
+  return tape
+
+
+def circuit_fitness(objective: str, max_qubits: int, max_depth: int, circuits, target=None, seed=None,
+                    penalize: bool = True, device=None) -> np.ndarray:
+  """fitness(individual) of evo/run.py:25-31 for a population: R - penalize*C of each whole circuit.
+
+  circuits: list of gate lists [(kind in {'p','rx','cp','cx'}, wire, control, theta)].  One replay launch
+  applies every circuit from |0..0> / I and terminates it; the reward of the Terminate step is
+  metric - cost (env.py:134-135 with sparse=True, punish=penalize)."""
+  dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+  n = len(circuits)
+  max_len = max(1, max(len(c) for c in circuits))
+  tgt = make_target(objective, max_qubits, seed) if target is None else target
+  batch = EnvBatch(n, max_qubits, max_depth, objective, tgt, punish=penalize, sparse=True, autoreset=False,
+                   obs_mode='none', track_episodes=False, fused_stats=False, device=dev)
+  tape = np.stack([encode_circuit(c, max_len) for c in circuits], axis=1)             # [T,N,4]
+  rec = {'reward': torch.zeros((max_len + 1, n), dtype=torch.float64, device=dev)}
+  batch.replay(torch.as_tensor(tape, device=dev), rec)
+  idx = torch.as_tensor([len(c) for c in circuits], device=dev)
+  return rec['reward'][idx, torch.arange(n, device=dev)].cpu().numpy()
