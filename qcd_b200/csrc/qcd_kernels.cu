@@ -1,32 +1,36 @@
-// qcd_kernels.cu — batched CircuitDesigner hot path for B200 (sm_100a).
+// qcd_kernels.cu — batched CircuitDesigner hot path for B200 (sm_100a) + the C-ABI of include/qcd_b200.h.
 //
-// One kernel template, two instantiation families:
-//   STAGED = false : the STEP kernel.  One launch = one env.step() of every env.  State is streamed
-//                    HBM -> registers -> HBM exactly once; the kernel is HBM-bound (32*S + 8*S + ~96
-//                    bytes per env-step, S = 2^eta (SP) or 4^eta (UC) complex128 amplitudes).
-//   STAGED = true  : the REPLAY kernel.  Each env's state is loaded into shared memory once, T actions
-//                    are applied in place, and it is written back once (FP64-pipe / smem bound).
+// Kernels (DESIGN.md §4 has the roofline and the measured numbers of each):
+//   step_warp_kernel   K1a  one env.step() of every env, S <= 128 amplitudes: a warp owns 32 envs,
+//                           lane-per-env decode, butterflies by shuffle, register prefetch, PDL.
+//   qcd_kernel<!STAGED> K1b the same step for S >= 256: pair-streaming, one warp = one env per CTA.
+//   replay_warp_kernel K2a  T steps in one launch, S <= 256: the warp's tile stays in shared memory
+//                           (cp.async.bulk in / out).
+//   replay_cta_kernel  K2b  T steps in one launch, S >= 512: one CTA per env, 64 KiB of state in smem,
+//                           decode-ahead table, one barrier per step.
+//   qcd_kernel<STAGED>      first replay version; kept as the path for per-env targets.
+//   reset_kernel, stats_kernel
+// One launch = one step (or one tape) of ALL envs; the step kernels are HBM-bound
+// (32*S + 8*S + ~96 bytes per env-step, S = 2^eta (SP) or 4^eta (UC) complex128 amplitudes).
 //
 // Reference semantics reproduced (file:line in /root/reference):
-//   qcd_gym/env.py:90-100   action decode <o,q,c,Phi>            -> decode_action()
-//   qcd_gym/env.py:83-84    gate applied to Statevector/Operator -> apply_pair() (incremental: the
-//                            reference re-simulates the whole circuit, same ops in the same order)
-//   qcd_gym/env.py:86,129   depth / operations / used wires, truncation -> decode_action()
+//   qcd_gym/env.py:90-100   action decode <o,q,c,Phi>            -> decode_kind(), decode_action()
+//   qcd_gym/env.py:83-84    gate applied to Statevector/Operator -> apply_pair() / mul_phase() / rot_rx()
+//                            (incremental: the reference re-simulates the whole circuit, same ops in the
+//                            same order)
+//   qcd_gym/env.py:86,129   depth / operations / used wires, truncation -> book_gate()
 //   qcd_gym/env.py:106-114  fidelity | arctan-Frobenius metric, depth cost -> finalize_step()
 //   qcd_gym/env.py:134-135  sparse / punish shaping                -> finalize_step()
-//   qcd_gym/env.py:10,85    float32 observation [Re | Im]          -> store phase of run_phase2()
+//   qcd_gym/env.py:10,85    float32 observation [Re | Im]          -> store phase of every kernel
 //   qcd_gym/env.py:117-121  reset                                   -> fused auto-reset + reset_kernel
-//   qcd_gym/wrappers/monitor.py:37-48 episode return/length        -> finalize_step(), stats_kernel
+//   qcd_gym/wrappers/monitor.py:37-48 episode return/length        -> phase3(), stats_kernel
 //
 // Mapping.  A gate on qubit w only couples amplitude pairs (i0, i1 = i0 | 1<<w).  Every gate of the
 // reference's set {P, RX, CP, CX} is a 2x2 butterfly on such a pair (CP/CX predicated on the control
-// bit of i0), so a group of L = 2^LOG2L threads owns one env and each thread owns PPT = S/2/L pairs;
-// pair k maps to i0 by inserting a zero bit at position w.  No thread ever needs another thread's
-// amplitudes, gates are heterogeneous per env for free (only the address pattern and two doubles
-// differ), and UC is the same butterfly on the row bits (w + eta) of the row-major unitary.
-// The per-env scalar work (floor-decode, sincos, depth stack, cost, reward) is done by ONE thread per
-// env with consecutive threads on consecutive envs (fully populated warps, coalesced scalar I/O) and
-// handed to the group through shared memory.
+// bit of i0); gates are heterogeneous per env for free (only the address / lane pattern and two
+// doubles differ), and UC is the same butterfly on the row bits (w + eta) of the row-major unitary.
+// The per-env scalar work (floor-decode, sincos, depth stack, cost, reward) is done by ONE lane per
+// env with consecutive lanes on consecutive envs (coalesced scalar I/O).
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -41,7 +45,7 @@ namespace qcd {
 #define QCD_REG_STEP_MAX_LOG2S 7     // S <= 128: warp-autonomous step kernel; above: pair-streaming
 #endif
 #ifndef QCD_STEP_IMPL
-#define QCD_STEP_IMPL 2                // small-S step path: 0 pair-streaming, 1 CTA register-resident, 2 warp-autonomous
+#define QCD_STEP_IMPL 2                // small-S step path: 0 pair-streaming, 2 warp-autonomous
 #endif
 #ifndef QCD_WARP_STEP_WARPS
 #define QCD_WARP_STEP_WARPS 1           // warps per CTA (each warp is autonomous; 1 balances best across 148 SMs)
@@ -91,9 +95,6 @@ namespace qcd {
 #ifndef QCD_WARP_STEP_STAGE
 #define QCD_WARP_STEP_STAGE 0         // 1: stage the tile in smem with cp.async.bulk (TMA) when it fits 16 KiB
                                      // (measured slower than the register prefetch on B200, kept as an option)
-#endif
-#ifndef QCD_REG_STEP_THREADS
-#define QCD_REG_STEP_THREADS 256
 #endif
 
 constexpr int K_NONE = 0, K_P = 1, K_RX = 2, K_CP = 3, K_CX = 4;
@@ -562,134 +563,6 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
     const long base = env0 * S;
     const long lim = (N - env0 < E ? N - env0 : E) * (long)S;
     for (long i = tid; i < lim; i += NT) gstate[base + i] = s_tile[i];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Register-resident STEP kernel for small states (S <= 256 amplitudes, i.e. <= 4 KiB per env).
-//
-// The pair-streaming kernel above cannot issue its state loads before the action is decoded (the
-// pair addresses depend on the wire), which serialises two DRAM latencies + a sincos behind a CTA
-// barrier.  Here the ownership of amplitudes is FIXED: lane l of the env's group of L lanes owns
-// amplitudes i = l + L*j (j < V), so every state / target load is issued at kernel entry, fully
-// coalesced (the L lanes of a group read L*16 contiguous bytes per j), and overlaps the decode.
-// The butterfly partner of amplitude i for wire bit w is then either in the same lane
-// (w >= log2 L: register j ^ 2^(w-log2 L), chosen with selects) or in lane l ^ 2^w (one shuffle).
-template <int LOG2S, bool UC, int LOG2L, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-step_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32) {
-  constexpr int S = 1 << LOG2S, L = 1 << LOG2L, E = NT / L, V = S / L;
-  constexpr int LOG2V = LOG2S - LOG2L;
-  static_assert(L <= 32 && V >= 1 && V <= 16, "register-resident step: group within a warp");
-  constexpr unsigned FULL = 0xffffffffu;
-
-  __shared__ GateRec s_rec[E];
-  __shared__ double2 s_red[E];
-
-  const int tid = threadIdx.x;
-  const long env0 = (long)blockIdx.x * E;
-  const long N = b.n_envs;
-  const int grp = tid >> LOG2L, lane = tid & (L - 1);
-  const long genv = env0 + grp;
-  const bool gact = genv < N;
-  const bool ctl = tid < E && env0 + tid < N;
-  const long cenv = env0 + tid;
-
-  // ---- all state / target loads first: they do not depend on the action
-  double2* st = reinterpret_cast<double2*>(b.state) + (gact ? genv * S : 0);
-  const double2* tg = reinterpret_cast<const double2*>(b.target) +
-                      (((b.flags & QCD_F_TARGET_PER_ENV) && gact) ? genv * S : 0);
-  double2 x[V], tv[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) x[j] = gact ? st[lane + L * j] : make_double2(0.0, 0.0);
-#pragma unroll
-  for (int j = 0; j < V; ++j) tv[j] = gact ? __ldg(tg + lane + L * j) : make_double2(0.0, 0.0);
-
-  // ---- phase 1: per-env scalar decode by the control threads (one env per thread)
-  EnvCtl e;
-  e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
-  if (ctl) {
-    double a0, a1, a2, a3;
-    load_action(actions, act_f32, cenv, a0, a1, a2, a3);
-    e.meta = reinterpret_cast<const uint4*>(b.meta)[cenv];
-    if (b.last) { const double2 l2 = reinterpret_cast<const double2*>(b.last)[cenv]; e.last_m = l2.x; e.last_c = l2.y; }
-    if (b.ep_return) { e.ep_ret = b.ep_return[cenv]; e.ep_len = b.ep_length[cenv]; }
-    GateRec rec;
-    decode_action(b, a0, a1, a2, a3, e, rec);
-    rec.flags |= RF_METRIC | RF_LAST;
-    s_rec[tid] = rec;
-  }
-  __syncthreads();
-
-  // ---- phase 2: butterflies in registers
-  GateRec g;
-  if (gact) g = s_rec[grp];
-  else { g.kind = K_NONE; g.wbit = 0; g.cbit = 0; g.flags = 0; g.cr = 1.0; g.sr = 0.0; }
-  const bool reset = g.flags & RF_RESET;
-  const bool lane_bit = g.wbit < LOG2L;                       // partner lives in another lane
-  const int src_lane = (tid & 31) ^ (lane_bit ? (1 << g.wbit) : 0);
-  const int jb = lane_bit ? 0 : (g.wbit - LOG2L);             // register bit of the wire otherwise
-  double2 y[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    // in-lane candidate: x[j ^ (1 << jb)] (selects over the compile-time register bits)
-    double2 p = x[j];
-    if (LOG2V > 0) {
-#pragma unroll
-      for (int bit = 0; bit < LOG2V; ++bit) {
-        const double2 cand = x[j ^ (1 << bit)];
-        const bool take = !lane_bit && jb == bit;
-        p.x = take ? cand.x : p.x; p.y = take ? cand.y : p.y;
-      }
-    }
-    // cross-lane partner (identity shuffle when the wire is a register bit); all lanes take part
-    p.x = __shfl_sync(FULL, p.x, src_lane);
-    p.y = __shfl_sync(FULL, p.y, src_lane);
-    const int i = lane + L * j;
-    const bool bw = (i >> g.wbit) & 1, bc = (i >> g.cbit) & 1;
-    double2 v = x[j];
-    switch (g.kind) {
-      case K_P:  if (bw) v = mul_phase(v, g.cr, g.sr); break;
-      case K_CP: if (bw && bc) v = mul_phase(v, g.cr, g.sr); break;
-      case K_RX: v = rot_rx(v, p, g.cr, g.sr); break;
-      case K_CX: if (bc) v = p; break;
-      default: break;
-    }
-    y[j] = v;
-  }
-  double ra = 0.0, rb = 0.0;
-#pragma unroll
-  for (int j = 0; j < V; ++j) metric_acc<UC>(y[j], tv[j], ra, rb);
-#pragma unroll
-  for (int off = L / 2; off >= 1; off >>= 1) {
-    ra += __shfl_xor_sync(FULL, ra, off);
-    rb += __shfl_xor_sync(FULL, rb, off);
-  }
-  if (lane == 0 && gact) s_red[grp] = make_double2(ra, rb);
-
-  if (gact) {
-    float* ob = b.obs ? b.obs + genv * b.obs_stride : nullptr;
-    float* fob = (b.final_obs && reset) ? b.final_obs + genv * b.obs_stride : nullptr;
-    const bool wr_state = g.kind != K_NONE || reset;
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const int i = lane + L * j;
-      if (fob) { fob[i] = (float)y[j].x; fob[S + i] = (float)y[j].y; }
-      const double2 v = reset ? reset_amp(UC, b.n_qubits, i) : y[j];
-      if (wr_state) st[i] = v;
-      if (ob) { ob[i] = (float)v.x; ob[S + i] = (float)v.y; }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3
-  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  phase3<UC, E>(b, none, e, ctl, cenv, 0, 1, N, tid, ctl ? s_red[tid] : make_double2(0.0, 0.0), ctl,
-                stats_slice(b, blockIdx.x));
-  if (ctl) {
-    reinterpret_cast<uint4*>(b.meta)[cenv] = e.meta;
-    if (b.last) reinterpret_cast<double2*>(b.last)[cenv] = make_double2(e.last_m, e.last_c);
-    if (b.ep_return) { b.ep_return[cenv] = e.ep_ret; b.ep_length[cenv] = e.ep_len; }
   }
 }
 
@@ -1559,18 +1432,6 @@ struct Launch {
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
       return (int)cudaLaunchKernelEx(&cfg, kern, b, actions, act_f32);
-    } else if constexpr (REG && QCD_STEP_IMPL == 1) {
-      constexpr int RNT = QCD_REG_STEP_THREADS;
-      constexpr int RL = clampi(S / 4, 1, 32);                // V = 4 amplitudes per lane (8 at S=256)
-      constexpr int RE = RNT / RL;
-#ifdef QCD_REG_MINB
-      constexpr int MINB = (S / RL) <= 4 ? QCD_REG_MINB : (512 / RNT);
-#else
-      constexpr int MINB = (S / RL) <= 4 ? (1024 / RNT) : (512 / RNT);
-#endif
-      const unsigned grid = (unsigned)((b.n_envs + RE - 1) / RE);
-      step_reg_kernel<LOG2S, UC, ilog2(RL), RNT, MINB><<<grid, RNT, 0, stream>>>(b, actions, act_f32);
-      return (int)cudaGetLastError();
     } else {
       return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
     }
