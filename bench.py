@@ -273,8 +273,10 @@ def run_native(args):
   obs_mode = args.obs
 
   # ---- R replicas of the batch so that consecutive launches never find their data in L2
+  from qcd_b200 import _lib as qlib
+  shared_stats = torch.zeros((qlib.STATS_COPIES, qlib.STATS_STRIDE), dtype=torch.float64, device=dev)
   probe = EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
-                   fused_stats=not args.no_stats, device=dev)
+                   fused_stats=not args.no_stats, device=dev, stats_buffer=shared_stats)
   S = probe.S
   bytes_step_env = probe.algorithmic_bytes_per_step()
   footprint = N * (16 * S + (8 * S if obs_mode != 'none' else 0) + 96)
@@ -283,7 +285,8 @@ def run_native(args):
   per_replica = N * (16 * S + (4 * probe.obs_stride if obs_mode != 'none' else 0) * (2 if args.final_obs else 1) + 200)
   R = max(1, min(R, int(0.8 * free // per_replica)))
   batches = [probe] + [EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
-                                fused_stats=not args.no_stats, device=dev) for _ in range(R - 1)]
+                                fused_stats=not args.no_stats, device=dev, stats_buffer=shared_stats)
+                       for _ in range(R - 1)]
   tape_np = make_tape(eta, TAPE_LEN if mode == 'step' else REPLAY_T * 2, N, seed=1234 + rank,
                       no_terminate=args.no_terminate)
   tape = torch.as_tensor(tape_np, device=dev)
@@ -299,29 +302,41 @@ def run_native(args):
     def launch(i):
       batches[i % R].replay(tape[(i % 2) * REPLAY_T:(i % 2 + 1) * REPLAY_T])
 
-  # ---- CUDA graph of G consecutive launches (launch-bound otherwise: ~20 us kernels)
+  # ---- CUDA graphs of consecutive launches (launch-bound otherwise: ~20 us kernels).  One graph of G
+  # launches (a whole number of replica/tape periods) plus, for step counts that are not a multiple
+  # of G, one graph per remainder, so that EVERY timed launch is replayed from a graph.
   G = int(np.lcm(R, TAPE_LEN)) if mode == 'step' else R * 2
-  G = min(G, max(1, K))
   stream = torch.cuda.Stream(dev)
-  graph = None
+  graphs = {}
+
+  def capture(n):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+      for i in range(n):
+        launch(i)
+    return g
+
   with torch.cuda.stream(stream):
     for i in range(max(W, 3)):
       launch(i)
     stream.synchronize()
     if not args.no_graph:
-      graph = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(graph, stream=stream):
-        for i in range(G):
-          launch(i)
-      graph.replay()
+      for n in {G, K % G, W % G} - {0}:
+        if n <= max(K, W):
+          graphs[n] = capture(n)
+          graphs[n].replay()
       stream.synchronize()
+  graph = graphs.get(G) or (next(iter(graphs.values())) if graphs else None)
 
   def run_steps(k):
     done = 0
-    if graph is not None:
+    if G in graphs:
       while done + G <= k:
-        graph.replay()
+        graphs[G].replay()
         done += G
+    if (k - done) in graphs:
+      graphs[k - done].replay()
+      done = k
     while done < k:
       launch(done)
       done += 1
@@ -329,6 +344,8 @@ def run_native(args):
   clocks = ClockSampler(local)
   with torch.cuda.stream(stream):
     run_steps(W)
+    # warm the (torch) reduction of the statistics replicas: its kernels are lazily loaded on first use
+    all_reduce_stats(shared_stats.sum(0))
     stream.synchronize()
     if world > 1:
       dist.barrier()
@@ -338,7 +355,7 @@ def run_native(args):
     ev0.record(stream)
     run_steps(K)
     # the one collective of the path: episode statistics of all ranks (96 B) over NCCL/NVLink
-    stats = torch.stack([b.stats for b in batches]).sum(0)
+    stats = shared_stats.sum(0)          # all replicas of this rank accumulate into one vector
     all_reduce_stats(stats)
     ev1.record(stream)
     stream.synchronize()
@@ -463,7 +480,7 @@ def run_native(args):
                  "cuda_graph": graph is not None, "graph_len": G if graph is not None else 0,
                  "steps_per_launch": steps_per_launch, "parallelism": f"env-sharded x{world}, stats all-reduce only"},
       "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu,
-      "episode_stats": summarize(stats), "sweep": sweep,
+      "episode_stats": summarize(stats[:qlib.STATS_LEN]), "sweep": sweep,
   }
   print(json.dumps(line), flush=True)
   if world > 1:

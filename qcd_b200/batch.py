@@ -38,7 +38,8 @@ class EnvBatch:
 
   def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str, target,
                punish: bool = True, sparse: bool = True, autoreset: bool = True, obs_mode: str = 'full',
-               final_obs: bool = False, track_episodes: bool = True, fused_stats: bool = True, device=None):
+               final_obs: bool = False, track_episodes: bool = True, fused_stats: bool = True, device=None,
+               stats_buffer: torch.Tensor | None = None):
     if not torch.cuda.is_available():
       raise RuntimeError("qcd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     self.lib = _lib.load_library()
@@ -84,7 +85,13 @@ class EnvBatch:
     self.terminated = torch.zeros(N, dtype=u8, device=dev)
     self.truncated = torch.zeros(N, dtype=u8, device=dev)
     self.status = torch.zeros(N, dtype=torch.int8, device=dev)
-    self._stats_raw = torch.zeros((_lib.STATS_COPIES, _lib.STATS_STRIDE), dtype=f64, device=dev)
+    if stats_buffer is None:
+      self._stats_raw = torch.zeros((_lib.STATS_COPIES, _lib.STATS_STRIDE), dtype=f64, device=dev)
+    else:                       # several batches of one job may accumulate into a common vector
+      if tuple(stats_buffer.shape) != (_lib.STATS_COPIES, _lib.STATS_STRIDE) or stats_buffer.dtype != f64 \
+          or stats_buffer.device != dev or not stats_buffer.is_contiguous():
+        raise ValueError("stats_buffer must be a contiguous float64 [STATS_COPIES, STATS_STRIDE] tensor on the env device")
+      self._stats_raw = stats_buffer
 
     self.obs = self.final_obs = None
     self.obs_stride = 2 * S
