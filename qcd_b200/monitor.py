@@ -1,63 +1,115 @@
-"""Monitor wrapper for the single-env API (reference: qcd_gym/wrappers/monitor.py:6-76).
+"""Episode monitor for the single-env API.
 
-Records episode return / length / wall time and the Q-metrics d,o,q,m,c into info['episode'] when
-an episode ends; refuses to step an env that needs a reset.  The vectorised env does the same
-bookkeeping on the device (ep_return / ep_length accumulators inside the step kernel)."""
+Behavioural contract taken from the reference wrapper (qcd_gym/wrappers/monitor.py:29-52): while an
+episode runs it records observations, actions and rewards; when `step` reports terminated or truncated
+it moves `termination_reason` out of `info` into its own history and attaches
+
+    info["episode"] = {r, l, t, history, d, o, q, m, c}
+
+(return rounded to 6 digits, length, wall time since construction, the recorded trajectory, and the
+final depth / operations / used wires / metric / cost); stepping again before `reset` raises
+RuntimeError.  The vectorised env keeps the same r/l accumulators on the device inside the step kernel.
+"""
 from __future__ import annotations
 
 import time
+from dataclasses import dataclass, field
 
 import numpy as np
 
 from .gym_compat import Wrapper
 
+_QMETRICS = {'d': 'depth', 'o': 'operations', 'q': 'used_wires', 'm': 'metric', 'c': 'cost'}
+
+
+@dataclass
+class _Trajectory:
+  states: list = field(default_factory=list)
+  actions: list = field(default_factory=list)
+  rewards: list = field(default_factory=list)
+
+  def snapshot(self) -> dict:
+    return {'states': list(self.states), 'actions': list(self.actions), 'rewards': list(self.rewards)}
+
 
 class Monitor(Wrapper):
-  def __init__(self, env, record_video=False):
+  def __init__(self, env, record_video: bool = False):
     super().__init__(env)
     self.t_start = time.time()
-    self.record_video = record_video; self._frame_buffer = []
-    self.states, self.actions, self.rewards = [], [], []
-    self._episode_returns, self._termination_reasons = [], []
-    self._episode_lengths, self._episode_times = [], []
-    self._total_steps = 0; self.needs_reset = True
+    self.record_video = record_video
+    self.needs_reset = True
+    self._traj = _Trajectory()
+    self._frames: list = []
+    self._log = {'returns': [], 'lengths': [], 'times': [], 'reasons': []}
+    self._total_steps = 0
 
-  def _history(self):
-    return {key: list(getattr(self, key)) for key in ('states', 'actions', 'rewards')}
+  # -- trajectory of the running episode, under the reference's attribute names
+  states = property(lambda self: self._traj.states)
+  actions = property(lambda self: self._traj.actions)
+  rewards = property(lambda self: self._traj.rewards)
+
+  def _grab_frame(self):
+    if self.record_video:
+      self._frames.append(self.render())
 
   def reset(self, **kwargs):
+    observation, info = self.env.reset(**kwargs)
+    self._traj = _Trajectory(states=[observation])
     self.needs_reset = False
-    state, info = self.env.reset(**kwargs)
-    self.rewards = []; self.states = [state]; self.actions = []
-    if self.record_video: self._frame_buffer.append(self.render())
-    return state, info
+    self._grab_frame()
+    return observation, info
 
   def step(self, action):
-    if self.needs_reset: raise RuntimeError("Tried to step environment that needs reset")
-    state, reward, terminated, truncated, info = self.env.step(action)
-    self.states.append(state); self.actions.append(action); self.rewards.append(float(reward))
-    if self.record_video: self._frame_buffer.append(self.render())
-    if terminated or truncated:
-      self.needs_reset = True
-      ep_rew, ep_len, now = sum(self.rewards), len(self.rewards), time.time() - self.t_start
-      self._episode_returns.append(ep_rew); self._episode_lengths.append(ep_len); self._episode_times.append(now)
-      self._termination_reasons.append(info.pop('termination_reason'))
-      info["episode"] = {"r": round(ep_rew, 6), "l": ep_len, "t": round(now, 6), 'history': self._history(),
-                         'd': info["depth"], 'o': info["operations"], 'q': info["used_wires"],
-                         'm': info["metric"], 'c': info["cost"]}
+    if self.needs_reset:
+      raise RuntimeError("Tried to step environment that needs reset")
+    observation, reward, terminated, truncated, info = self.env.step(action)
+    traj = self._traj
+    traj.states.append(observation); traj.actions.append(action); traj.rewards.append(float(reward))
+    self._grab_frame()
     self._total_steps += 1
-    return state, reward, terminated, truncated, info
+    if terminated or truncated:
+      self._close_episode(info)
+    return observation, reward, terminated, truncated, info
 
-  def get_video(self, reset=True):
-    frames = list(self._frame_buffer)
-    if reset: self._frame_buffer = []
-    return np.array(frames)
+  def _close_episode(self, info: dict) -> None:
+    elapsed = time.time() - self.t_start
+    total, length = sum(self._traj.rewards), len(self._traj.rewards)
+    log = self._log
+    log['returns'].append(total); log['lengths'].append(length); log['times'].append(elapsed)
+    log['reasons'].append(info.pop('termination_reason'))
+    episode = {'r': round(total, 6), 'l': length, 't': round(elapsed, 6), 'history': self._traj.snapshot()}
+    episode.update({short: info[key] for short, key in _QMETRICS.items()})
+    info['episode'] = episode
+    self.needs_reset = True
+
+  # -- video helpers (text mode only, like the reference's write_video)
+  def get_video(self, reset: bool = True):
+    frames = np.array(self._frames)
+    if reset:
+      self._frames = []
+    return frames
 
   def write_video(self, writer, label, step):
-    if self.render_mode == 'text': writer.add_text(label, str(self.env.render()), step)
+    if self.render_mode == 'text':
+      writer.add_text(label, str(self.env.render()), step)
 
-  total_steps = property(lambda self: self._total_steps)
-  episode_returns = property(lambda self: self._episode_returns)
-  termination_reasons = property(lambda self: self._termination_reasons)
-  episode_lengths = property(lambda self: self._episode_lengths)
-  episode_times = property(lambda self: self._episode_times)
+  # -- accumulated history
+  @property
+  def total_steps(self) -> int:
+    return self._total_steps
+
+  @property
+  def episode_returns(self) -> list:
+    return self._log['returns']
+
+  @property
+  def episode_lengths(self) -> list:
+    return self._log['lengths']
+
+  @property
+  def episode_times(self) -> list:
+    return self._log['times']
+
+  @property
+  def termination_reasons(self) -> list:
+    return self._log['reasons']
