@@ -7,7 +7,7 @@ from hypothesis import given, settings, strategies as st
 from oracle.batch_oracle import OracleBatch
 from oracle.qcd_oracle import OracleCircuitDesigner, make_target
 
-f32 = lambda lo, hi: st.floats(min_value=lo, max_value=hi, width=32, allow_nan=False)
+f32 = lambda lo, hi: st.floats(min_value=float(np.float32(lo)), max_value=float(np.float32(hi)), width=32, allow_nan=False)
 
 
 def actions(eta, n):
