@@ -53,6 +53,18 @@ namespace qcd {
 #ifndef QCD_WARP_STEP_MINB
 #define QCD_WARP_STEP_MINB 16          // min CTAs per SM for __launch_bounds__ (caps registers at 128)
 #endif
+#ifndef QCD_WARP_BRANCHLESS
+#define QCD_WARP_BRANCHLESS 1           // branch-free round body (select instead of switch) ...
+#endif
+#ifndef QCD_WARP_BRANCHLESS_MAX_V
+#define QCD_WARP_BRANCHLESS_MAX_V 2     // ... for at most this many amplitudes per lane (S <= 64)
+#endif
+#ifndef QCD_WARP_LOG2L_S32
+#define QCD_WARP_LOG2L_S32 5            // log2(lanes per env) of the warp kernels at S = 32
+#endif
+#ifndef QCD_WARP_LOG2L_S64
+#define QCD_WARP_LOG2L_S64 5            // ... at S = 64
+#endif
 #ifndef QCD_PAIR_SMALL_MAX_S
 #define QCD_PAIR_SMALL_MAX_S 4096
 #endif
@@ -780,7 +792,8 @@ __device__ __forceinline__ void fence_async_smem() {
 template <int LOG2S, int TE, bool STAGE>
 struct WarpCfg {
   static constexpr int S = 1 << LOG2S;
-  static constexpr int LOG2L = LOG2S < 5 ? LOG2S : 5, L = 1 << LOG2L;
+  static constexpr int LOG2L = LOG2S == 5 ? QCD_WARP_LOG2L_S32 : (LOG2S == 6 ? QCD_WARP_LOG2L_S64 : (LOG2S < 5 ? LOG2S : 5));
+  static constexpr int L = 1 << LOG2L;
   static constexpr int V = S / L, LOG2V = LOG2S - LOG2L;
   static constexpr int G = 32 / L, LOG2G = 5 - LOG2L;       // envs per round
   static constexpr int R = TE / G;                         // rounds per tile
@@ -963,6 +976,54 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
         const int src = (c0 + k) * G + gi;        // decode lane / tile-local env of this group
         const double2 cs = s_cs[src];
         const int pk = s_pk[src];
+        if constexpr (QCD_WARP_BRANCHLESS && V <= QCD_WARP_BRANCHLESS_MAX_V) {
+        // Branch-free round: both candidate results are computed and selected, the partner shuffle is
+        // unconditional, stores are predicated.  One basic block per group of PF rounds, so the
+        // scheduler can interleave independent rounds (the warp has few siblings to hide latency).
+        const int kind = pk & 7;
+        const bool reset = pk & 8;
+        const unsigned wm = (pk >> 11) & 0xffu, cm = (pk >> 19) & 0xffu;
+        const bool act = src < n_valid;
+        const bool is_rx = kind == K_RX, is_cx = kind == K_CX;
+        const unsigned pm = (kind == K_P) ? wm : ((kind == K_CP) ? (wm | cm) : 0x100u);   // 0x100: never
+        const int src_lane = lane ^ ((pk >> 4) & 31);
+        const int jsel = (pk >> 9) & 3;
+        double ra, rb;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const unsigned i = li + L * j;
+          const double2 v = cur[u][j];
+          double2 p = v;
+          if (LOG2V > 0) {
+#pragma unroll
+            for (int bit = 0; bit < LOG2V; ++bit) {
+              const double2 cand = cur[u][j ^ (1 << bit)];
+              const bool take = jsel == bit + 1;
+              p.x = take ? cand.x : p.x; p.y = take ? cand.y : p.y;
+            }
+          }
+          p.x = __shfl_sync(FULL, p.x, src_lane);
+          p.y = __shfl_sync(FULL, p.y, src_lane);
+          const bool ph = (i & pm) == pm;
+          const bool cxs = is_cx && (i & cm);
+          const double2 m = mul_phase(v, cs.x, cs.y);
+          const double2 x = rot_rx(v, p, cs.x, cs.y);
+          double2 y = v;
+          y.x = ph ? m.x : y.x; y.y = ph ? m.y : y.y;
+          y.x = is_rx ? x.x : y.x; y.y = is_rx ? x.y : y.y;
+          y.x = cxs ? p.x : y.x; y.y = cxs ? p.y : y.y;
+          if (j == 0) metric_set<UC>(y, tv[j], ra, rb); else metric_acc<UC>(y, tv[j], ra, rb);
+          const bool wr = act && (ph || is_rx || cxs || reset);
+          if (act && reset && fp) {
+            float* f = fp + (long)(c0 + k) * gstride;
+            f[L * j] = (float)y.x; f[S + L * j] = (float)y.y;
+          }
+          const double2 o2 = make_double2(reset ? rv[j] : y.x, reset ? 0.0 : y.y);
+          if (wr) sp[k * G * S + L * j] = o2;
+          if (act && op) { op[L * j] = (float)o2.x; op[S + L * j] = (float)o2.y; }
+        }
+        part[k * ROW + lane] = make_double2(ra, rb);
+        } else {
         const int kind = pk & 7;
         const bool reset = pk & 8;
         const unsigned wm = (pk >> 11) & 0xffu, cm = (pk >> 19) & 0xffu;
@@ -1034,6 +1095,7 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
               if (op) { op[L * j] = (float)y[j].x; op[S + L * j] = (float)y[j].y; }
             }
           }
+        }
         }
         if (op) op += gstride;
       }
