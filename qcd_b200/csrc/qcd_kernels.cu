@@ -53,6 +53,15 @@ namespace qcd {
 #ifndef QCD_WARP_STEP_MINB
 #define QCD_WARP_STEP_MINB 16          // min CTAs per SM for __launch_bounds__ (caps registers at 128)
 #endif
+#ifndef QCD_WARP_PF_V1
+#define QCD_WARP_PF_V1 8                // rounds of state prefetched in registers when V == 1
+#endif
+#ifndef QCD_WARP_PF_V2
+#define QCD_WARP_PF_V2 2
+#endif
+#ifndef QCD_WARP_PF_V4
+#define QCD_WARP_PF_V4 2
+#endif
 #ifndef QCD_WARP_BRANCHLESS
 #define QCD_WARP_BRANCHLESS 1           // branch-free round body (select instead of switch) ...
 #endif
@@ -798,7 +807,7 @@ struct WarpCfg {
   static constexpr int G = 32 / L, LOG2G = 5 - LOG2L;       // envs per round
   static constexpr int R = TE / G;                         // rounds per tile
   static constexpr int C = R < 8 ? R : 8;                  // rounds per reduction chunk
-  static constexpr int PF0 = V == 1 ? 4 : (V <= 4 ? 2 : 1);
+  static constexpr int PF0 = V == 1 ? QCD_WARP_PF_V1 : (V == 2 ? QCD_WARP_PF_V2 : (V <= 4 ? QCD_WARP_PF_V4 : 1));
   static constexpr int PF = STAGE ? 1 : (PF0 < C ? PF0 : C);   // rounds of state in flight in registers
   static constexpr int ROW = 36;                           // double2 slots per scratch row
   static constexpr int SUMS = C * G, P = 32 / SUMS, VAL = L / P;
