@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 3
+#define QCD_ABI_VERSION 4
 
 #define QCD_MAX_QUBITS_SP 12   /* S = 4096 complex128 = 64 KiB per env */
 #define QCD_MAX_QUBITS_UC 6    /* 64x64 unitary      = 64 KiB per env */
@@ -150,12 +150,26 @@ int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int3
  * qcd_step / qcd_replay fuse when b->stats != NULL (do not use both on the same vector). */
 int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream);
 
-/* Host-buffer convenience used by the end-to-end path: copy `actions_host` (pinned) to
- * `actions_dev`, run qcd_step, copy reward/terminated/truncated (and obs rows, 2*S floats each,
- * when obs_host != NULL) back to host buffers; all on `stream`, no synchronisation. */
+/* HOST (pinned) destinations of qcd_step_host; every pointer may be NULL (field not copied back). */
+typedef struct qcd_host_out {
+  double*  reward;          /* [N] */
+  double*  metric;          /* [N] */
+  double*  cost;            /* [N] */
+  int32_t* depth;           /* [N] */
+  int32_t* operations;      /* [N] */
+  int32_t* used_wires;      /* [N] */
+  uint8_t* terminated;      /* [N] */
+  uint8_t* truncated;       /* [N] */
+  int8_t*  status;          /* [N] */
+  float*   obs;             /* rows of 2*S floats (the state half), obs_stride floats apart */
+  int64_t  obs_stride;
+} qcd_host_out_t;
+
+/* The reference's call with HOST buffers (env.step(action) -> obs, reward, terminated, truncated, info,
+ * env.py:124-136): copy `actions_host` (pinned) to `actions_dev`, run qcd_step, copy the requested
+ * results back into `out`'s host buffers; all on `stream`, no synchronisation (the caller syncs once). */
 int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_dev, int action_dtype,
-                  double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
-                  float* obs_host, int64_t obs_host_stride, void* stream);
+                  const qcd_host_out_t* out, void* stream);
 
 #ifdef __cplusplus
 }

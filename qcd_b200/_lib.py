@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 STATS_LEN = 12
 STATS_COPIES = 64
 STATS_STRIDE = 16
@@ -46,6 +46,13 @@ class QcdTapeOut(C.Structure):
               ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("status", C.c_void_p)]
 
 
+class QcdHostOut(C.Structure):
+  """Mirror of `qcd_host_out_t` (host destinations of qcd_step_host)."""
+  _fields_ = [("reward", C.c_void_p), ("metric", C.c_void_p), ("cost", C.c_void_p), ("depth", C.c_void_p),
+              ("operations", C.c_void_p), ("used_wires", C.c_void_p), ("terminated", C.c_void_p),
+              ("truncated", C.c_void_p), ("status", C.c_void_p), ("obs", C.c_void_p), ("obs_stride", C.c_int64)]
+
+
 EXPORTS = ("qcd_abi_version", "qcd_reset", "qcd_step", "qcd_replay", "qcd_reduce_stats", "qcd_step_host")
 
 _lib = None
@@ -73,8 +80,7 @@ def load_library(path: str | None = None) -> C.CDLL:
   lib.qcd_reduce_stats.restype = C.c_int
   lib.qcd_reduce_stats.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p]
   lib.qcd_step_host.restype = C.c_int
-  lib.qcd_step_host.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+  lib.qcd_step_host.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(QcdHostOut), C.c_void_p]
   if lib.qcd_abi_version() != ABI_VERSION:
     raise RuntimeError(f"libqcd_b200.so ABI {lib.qcd_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
   if path is None:

@@ -247,8 +247,8 @@ __device__ __forceinline__ StepOut finalize_step(const qcd_batch_t& b, EnvCtl& e
     const double nrm = sqrt(ra);                               // ||U - V||_F
     metric_raw = 1.0 - 2.0 * atan(nrm) / CUDART_PI;            // env.py:111
   } else {
-    const double h = hypot(ra, rb);                            // abs(vdot)
-    metric_raw = h * h;                                        // env.py:109
+    metric_raw = ra * ra + rb * rb;                            // env.py:109: abs(vdot)**2 (hypot-free:
+                                                               // within 2 ulp of numpy's hypot(re,im)**2)
   }
   if (!have_metric) metric_raw = CUDART_NAN;
   StepOut o;
@@ -1610,29 +1610,33 @@ int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream) {
 }
 
 int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_dev, int action_dtype,
-                  double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
-                  float* obs_host, int64_t obs_host_stride, void* stream) {
+                  const qcd_host_out_t* out, void* stream) {
   int rc = qcd::validate(b, true, actions_dev, action_dtype);
   if (rc) return rc;
-  if (!actions_host || !reward_host || !terminated_host || !truncated_host) return QCD_E_NULL;
+  if (!actions_host || !out) return QCD_E_NULL;
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t abytes = (size_t)b->n_envs * 4 * (action_dtype == QCD_ACT_F32 ? 4 : 8);
+  const size_t n = (size_t)b->n_envs;
+  const size_t abytes = n * 4 * (action_dtype == QCD_ACT_F32 ? 4 : 8);
   cudaError_t err = cudaMemcpyAsync(actions_dev, actions_host, abytes, cudaMemcpyHostToDevice, s);
   if (err != cudaSuccess) return (int)err;
   rc = qcd_step(b, actions_dev, action_dtype, stream);
   if (rc) return rc;
-  const size_t n = (size_t)b->n_envs;
-  err = cudaMemcpyAsync(reward_host, b->reward, n * sizeof(double), cudaMemcpyDeviceToHost, s);
-  if (err != cudaSuccess) return (int)err;
-  err = cudaMemcpyAsync(terminated_host, b->terminated, n, cudaMemcpyDeviceToHost, s);
-  if (err != cudaSuccess) return (int)err;
-  err = cudaMemcpyAsync(truncated_host, b->truncated, n, cudaMemcpyDeviceToHost, s);
-  if (err != cudaSuccess) return (int)err;
-  if (obs_host) {
+  const struct { void* dst; const void* src; size_t bytes; } copies[] = {
+      {out->reward, b->reward, n * sizeof(double)},        {out->metric, b->metric, n * sizeof(double)},
+      {out->cost, b->cost, n * sizeof(double)},            {out->depth, b->depth, n * sizeof(int32_t)},
+      {out->operations, b->operations, n * sizeof(int32_t)}, {out->used_wires, b->used_wires, n * sizeof(int32_t)},
+      {out->terminated, b->terminated, n},                 {out->truncated, b->truncated, n},
+      {out->status, b->status, n}};
+  for (const auto& c : copies) {
+    if (!c.dst) continue;
+    err = cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return (int)err;
+  }
+  if (out->obs) {
     if (!b->obs) return QCD_E_NULL;
     const int64_t S = b->objective == QCD_OBJ_UC ? (1LL << (2 * b->n_qubits)) : (1LL << b->n_qubits);
-    if (obs_host_stride < 2 * S) return QCD_E_STRIDE;
-    err = cudaMemcpy2DAsync(obs_host, (size_t)obs_host_stride * sizeof(float), b->obs,
+    if (out->obs_stride < 2 * S) return QCD_E_STRIDE;
+    err = cudaMemcpy2DAsync(out->obs, (size_t)out->obs_stride * sizeof(float), b->obs,
                             (size_t)b->obs_stride * sizeof(float), (size_t)(2 * S) * sizeof(float), n,
                             cudaMemcpyDeviceToHost, s);
     if (err != cudaSuccess) return (int)err;

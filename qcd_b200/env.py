@@ -2,18 +2,16 @@
 
 Drop-in for /root/reference/qcd_gym/env.py:13-141: same constructor kwargs, attributes, spaces,
 `reset` / `step` / `render` signatures, observation layout, info keys and exceptions.  The state
-lives on the GPU as an `EnvBatch` of one env (autoreset off); every `step` is one `qcd_step`
-launch followed by a read-back of the observation and the scalars.
+lives on the GPU as a vector env of one env (autoreset off); every `step` is one `qcd_step_host`
+call (H2D action, step kernel, D2H of the observation and the scalars) and one synchronisation.
 """
 from __future__ import annotations
 
 import numpy as np
-import torch
 
-from .batch import EnvBatch
 from .gym_compat import Box, Env, np_random
 from .targets import make_target
-from .vector_env import GATES, action_space_for
+from .vector_env import GATES, CircuitDesignerVectorEnv, action_space_for
 
 
 class CircuitDesigner(Env):
@@ -34,22 +32,15 @@ class CircuitDesigner(Env):
     self.punish = punish; self.sparse = sparse
     self.objective = objective
     self.target = make_target(objective, max_qubits, seed)                        # env.py:40
-    self._batch = EnvBatch(1, max_qubits, max_depth, objective, self.target, punish=punish, sparse=sparse,
-                           autoreset=False, obs_mode='full', track_episodes=False, device=device)
+    self._venv = CircuitDesignerVectorEnv(1, max_qubits, max_depth, objective, punish=punish, sparse=sparse,
+                                          target=self.target, device=device, autoreset=False)
+    self._batch = self._venv.batch
     self._ops = []                         # host mirror of the circuit, used by render() only
     b = self._batch
-    self._action_dev = torch.zeros((1, 4), dtype=torch.float64, device=b.device)
-    self._action_host = torch.zeros((1, 4), dtype=torch.float64, pin_memory=True)
     self.observation_space = Box(low=-1.0, high=+1.0, shape=(4 * b.S,))           # env.py:44
     self.action_space = action_space_for(self.qubits)                             # env.py:46-49
 
   # ------------------------------------------------------------------------------------------
-  def _read(self):
-    b = self._batch
-    obs = b.obs[0].cpu().numpy()
-    info = {'depth': int(b.depth[0]), 'operations': int(b.operations[0]), 'used_wires': int(b.used_wires[0])}
-    return obs, info
-
   def _operation(self, action):
     """env.py:90-100: host-side replica of the decode, for the exceptions and for render()."""
     gate, wire, cntrl, theta = action
@@ -64,23 +55,23 @@ class CircuitDesigner(Env):
 
   def reset(self, seed=None, options=None):
     super().reset(seed=seed)
-    self._batch.reset()
+    obs, _ = self._venv.reset()
     self._ops = []
-    return self._read()
+    return obs[0].cpu().numpy(), {'depth': 0, 'operations': 0, 'used_wires': 0}
 
   def step(self, action):
     operation = self._operation(action)              # raises AssertionError like env.py:94,100
     if operation is not None: self._ops.append(operation)
-    self._action_host[0] = torch.as_tensor(np.asarray(action, dtype=np.float64))
-    self._action_dev.copy_(self._action_host, non_blocking=True)
-    b = self._batch
-    b.step(self._action_dev)
-    state, info = self._read()
-    terminated, truncated = bool(b.terminated[0]), bool(b.truncated[0])
+    # one C-ABI call (H2D action, step kernel, D2H of the observation and every scalar) + one sync
+    obs, reward, term, trunc, inf = self._venv.step_host(np.asarray(action, dtype=np.float64).reshape(1, 4),
+                                                        copy_info=True)
+    terminated, truncated = bool(term[0]), bool(trunc[0])
+    info = {'depth': int(inf['depth'][0]), 'operations': int(inf['operations'][0]),
+            'used_wires': int(inf['used_wires'][0])}
     if terminated: info['termination_reason'] = 'DONE'
     if truncated: info['termination_reason'] = 'DEPTH'                            # env.py:130-131
-    info = {**info, 'metric': float(b.metric[0]), 'cost': float(b.cost[0])}
-    return state, float(b.reward[0]), terminated, truncated, info
+    info = {**info, 'metric': float(inf['metric'][0]), 'cost': float(inf['cost'][0])}
+    return obs[0].copy(), float(reward[0]), terminated, truncated, info
 
   # ------------------------------------------------------------------------------------------
   def render(self):

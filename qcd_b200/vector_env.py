@@ -103,40 +103,56 @@ class CircuitDesignerVectorEnv:
           'actions': torch.zeros((N, 4), dtype=action_dtype, **pin),
           'actions_dev': torch.zeros((N, 4), dtype=action_dtype, device=self.device),
           'reward': torch.zeros(N, dtype=torch.float64, **pin),
+          'metric': torch.zeros(N, dtype=torch.float64, **pin),
+          'cost': torch.zeros(N, dtype=torch.float64, **pin),
+          'depth': torch.zeros(N, dtype=torch.int32, **pin),
+          'operations': torch.zeros(N, dtype=torch.int32, **pin),
+          'used_wires': torch.zeros(N, dtype=torch.int32, **pin),
           'terminated': torch.zeros(N, dtype=torch.uint8, **pin),
           'truncated': torch.zeros(N, dtype=torch.uint8, **pin),
+          'status': torch.zeros(N, dtype=torch.int8, **pin),
           'obs': None,
       }
       if b.obs is not None:
         host['obs'] = torch.zeros((N, b.obs_stride), dtype=torch.float32, **pin)
         if b.obs_mode == 'full':
           host['obs'][:, 2 * b.S:] = b.obs[0, 2 * b.S:].cpu()
+      ptr = lambda k: host[k].data_ptr()
+      host['out_min'] = _lib.QcdHostOut(reward=ptr('reward'), terminated=ptr('terminated'), truncated=ptr('truncated'),
+                                        obs_stride=b.obs_stride)
+      host['out_all'] = _lib.QcdHostOut(**{k: ptr(k) for k in ('reward', 'metric', 'cost', 'depth', 'operations',
+                                                               'used_wires', 'terminated', 'truncated', 'status')},
+                                        obs_stride=b.obs_stride)
       self._host = host
     return self._host
 
-  def step_host(self, actions, copy_obs: bool = True):
+  def step_host(self, actions, copy_obs: bool = True, copy_info: bool = False):
     """The end-to-end call with HOST buffers: numpy actions in, numpy results out.
 
     H2D copy of the actions, the step kernel and the D2H copies of reward / terminated / truncated
-    (and the state half of every observation row) are issued on the current stream by
-    `qcd_step_host`, followed by one stream synchronisation.  Returned arrays are views of pinned
-    host buffers that the next call overwrites."""
+    (and the state half of every observation row; with copy_info also metric, cost, depth,
+    operations, used_wires, status) are issued on the current stream by `qcd_step_host`, followed by
+    one stream synchronisation.  Returned arrays are views of pinned host buffers that the next call
+    overwrites.  Returns (obs, reward, terminated, truncated[, info])."""
     a = np.asarray(actions)
     dt = torch.float64 if a.dtype == np.float64 else torch.float32
     h = self._host_buffers(dt)
     h['actions'].numpy()[...] = a.reshape(self.num_envs, 4)
     b = self.batch
     obs_h = h['obs'] if (copy_obs and h['obs'] is not None) else None
+    out = h['out_all'] if copy_info else h['out_min']
+    out.obs = None if obs_h is None else obs_h.data_ptr()
     stream = torch.cuda.current_stream(self.device)
     with torch.cuda.device(self.device):
       _lib.check(b.lib.qcd_step_host(
           b._cref, h['actions'].data_ptr(), h['actions_dev'].data_ptr(),
-          _lib.ACT_F64 if dt == torch.float64 else _lib.ACT_F32,
-          h['reward'].data_ptr(), h['terminated'].data_ptr(), h['truncated'].data_ptr(),
-          None if obs_h is None else obs_h.data_ptr(), b.obs_stride, stream.cuda_stream), "qcd_step_host")
+          _lib.ACT_F64 if dt == torch.float64 else _lib.ACT_F32, out, stream.cuda_stream), "qcd_step_host")
     stream.synchronize()
-    return (None if obs_h is None else obs_h.numpy(), h['reward'].numpy(),
-            h['terminated'].numpy().view(np.bool_), h['truncated'].numpy().view(np.bool_))
+    res = (None if obs_h is None else obs_h.numpy(), h['reward'].numpy(),
+           h['terminated'].numpy().view(np.bool_), h['truncated'].numpy().view(np.bool_))
+    if copy_info:
+      res += ({k: h[k].numpy() for k in ('metric', 'cost', 'depth', 'operations', 'used_wires', 'status')},)
+    return res
 
   def host_bytes_per_step(self, action_dtype=np.float32, copy_obs: bool = True):
     """(h2d, d2h) bytes `step_host` moves per call."""
