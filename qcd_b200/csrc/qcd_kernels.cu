@@ -101,8 +101,11 @@ namespace qcd {
 #ifndef QCD_WARP_REPLAY_TILE_BYTES
 #define QCD_WARP_REPLAY_TILE_BYTES 8192
 #endif
+#ifndef QCD_REPLAY_FUSE
+#define QCD_REPLAY_FUSE 1               // replay_cta_kernel: two consecutive gates per sweep over the state
+#endif
 #ifndef QCD_REPLAY_MINB
-#define QCD_REPLAY_MINB 3
+#define QCD_REPLAY_MINB 2                // CTAs/SM the 64-KiB replay kernel is compiled for (3 fit in smem but spill)
 #endif
 #ifndef QCD_REPLAY_CTA
 #define QCD_REPLAY_CTA 1                // replay for S >= 512: CTA per env with decode-ahead (0: first version)
@@ -645,20 +648,147 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
     }
     __syncthreads();                                          // table (and, first time, the state) ready
     const int nsteps = (T - t0) < NT ? (T - t0) : NT;
+    // thread 0: env.py:106-114,133-135 + Monitor + records of step t (uses e as booked for step t)
+    auto finalize0 = [&](const int t, const bool want_metric, const double xa, const double xb) {
+      const bool done = (e.status == QCD_ST_OK) && (e.term || e.trunc);
+      const StepOut o = finalize_step<UC>(b, e, xa, xb, want_metric);
+      if (out.reward) out.reward[(long)t * N + env] = o.reward;
+      if (out.metric) out.metric[(long)t * N + env] = o.metric;
+      if (out.cost) out.cost[(long)t * N + env] = o.cost;
+      if (out.depth) out.depth[(long)t * N + env] = e.depth;
+      if (out.terminated) out.terminated[(long)t * N + env] = e.term;
+      if (out.truncated) out.truncated[(long)t * N + env] = e.trunc;
+      if (out.status) out.status[(long)t * N + env] = (int8_t)e.status;
+      if (t == T - 1) {
+        b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
+        b.depth[env] = e.depth; b.operations[env] = e.ops; b.used_wires[env] = e.used_cnt;
+        b.terminated[env] = e.term; b.truncated[env] = e.trunc; b.status[env] = (int8_t)e.status;
+      }
+      if (stats) {
+        if (e.status != QCD_ST_OK) atomicAdd(stats + QCD_STAT_BAD_ACTIONS, 1.0);
+        else atomicAdd(stats + QCD_STAT_STEPS, 1.0);
+      }
+      if (done) {
+        if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
+        if (stats) {
+          atomicAdd(stats + QCD_STAT_EPISODES, 1.0);
+          if (b.ep_return) { atomicAdd(stats + QCD_STAT_SUM_R, e.ep_ret); atomicAdd(stats + QCD_STAT_SUM_L, (double)e.ep_len); }
+          atomicAdd(stats + QCD_STAT_SUM_D, (double)e.depth); atomicAdd(stats + QCD_STAT_SUM_O, (double)e.ops);
+          atomicAdd(stats + QCD_STAT_SUM_Q, (double)e.used_cnt);
+          atomicAdd(stats + QCD_STAT_SUM_M, o.metric); atomicAdd(stats + QCD_STAT_SUM_C, o.cost);
+          atomicAdd(stats + (e.trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE), 1.0);
+        }
+        if (autoreset) { e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0; }
+      }
+    };
+    auto unpack = [&](const StepRec& r, GateRec& g, int& status, bool& term, int& w, int& c) {
+      const int kind = r.pk & 7;
+      w = (r.pk >> 3) & 15; c = (r.pk >> 7) & 15; status = (r.pk >> 11) & 3; term = (r.pk >> 13) & 1;
+      g.cr = r.cr; g.sr = r.sr; g.kind = kind; g.wbit = w + shift; g.cbit = c + shift; g.flags = 0;
+    };
+    auto block_sums = [&](double ra, double rb) {            // warp partials ride on the step barrier
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        ra += __shfl_xor_sync(0xffffffffu, ra, off);
+        rb += __shfl_xor_sync(0xffffffffu, rb, off);
+      }
+      if ((tid & 31) == 0) s_wred[par][tid >> 5] = make_double2(ra, rb);
+    };
+    auto read_sums = [&](double& xa, double& xb) {
+      xa = 0.0; xb = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < NT / 32; ++wv) { xa += s_wred[par][wv].x; xb += s_wred[par][wv].y; }
+    };
+
 #pragma unroll 1
-    for (int si = 0; si < nsteps; ++si) {
+    for (int si = 0; si < nsteps;) {
       const int t = t0 + si;
-      const StepRec r = s_tab[si];
-      const int kind = r.pk & 7, w = (r.pk >> 3) & 15, c = (r.pk >> 7) & 15, status = (r.pk >> 11) & 3;
-      const bool term = (r.pk >> 13) & 1;
-      book_gate(b, status, kind, w, c, term, e);              // identical in every thread
+      GateRec g;
+      int status, w, c;
+      bool term;
+      unpack(s_tab[si], g, status, term, w, c);
+      book_gate(b, status, g.kind, w, c, term, e);            // identical in every thread
       const bool done = (status == QCD_ST_OK) && (e.term || e.trunc);
       const bool reset = done && autoreset;
       const bool want_metric = metric_every_step || done || t == T - 1;
-      GateRec g;
-      g.cr = r.cr; g.sr = r.sr; g.kind = kind; g.wbit = w + shift; g.cbit = c + shift; g.flags = 0;
+
+      if (QCD_REPLAY_FUSE && !want_metric && si + 1 < nsteps) {
+        // ---- fused pass: light step t (no metric, no reset) + step t+1 in ONE sweep over the state.
+        // Both gates are applied in registers to the 4 amplitudes closed under the two wire bits
+        // (or to the pair when the wires coincide / one step is a no-op).
+        if (tid == 0) finalize0(t, false, 0.0, 0.0);
+        GateRec g2;
+        int status2, w2, c2;
+        bool term2;
+        unpack(s_tab[si + 1], g2, status2, term2, w2, c2);
+        book_gate(b, status2, g2.kind, w2, c2, term2, e);
+        const bool done2 = (status2 == QCD_ST_OK) && (e.term || e.trunc);
+        const bool reset2 = done2 && autoreset;
+        const bool want2 = metric_every_step || done2 || t + 1 == T - 1;
+        double ra = 0.0, rb = 0.0;
+        if (g.kind == K_NONE || g2.kind == K_NONE || g.wbit == g2.wbit) {
+          const int wbit = (g.kind != K_NONE) ? g.wbit : g2.wbit;
+          const unsigned lowmask = (1u << wbit) - 1u;
+          const int wb = 1 << wbit;
+          if (g.kind != K_NONE || g2.kind != K_NONE || want2 || reset2) {
+#pragma unroll 2
+            for (int j = 0; j < PPT; ++j) {
+              const unsigned k = (unsigned)(tid + NT * j);
+              const int i0 = (int)(((k & ~lowmask) << 1) | (k & lowmask));
+              double2 x0 = s_state[i0], x1 = s_state[i0 | wb];
+              apply_pair(g, i0, x0, x1);
+              apply_pair(g2, i0, x0, x1);
+              if (want2) {
+                metric_acc<UC>(x0, __ldg(tgt + i0), ra, rb);
+                metric_acc<UC>(x1, __ldg(tgt + (i0 | wb)), ra, rb);
+              }
+              if (reset2) { x0 = reset_amp(UC, b.n_qubits, i0); x1 = reset_amp(UC, b.n_qubits, i0 | wb); }
+              s_state[i0] = x0; s_state[i0 | wb] = x1;
+            }
+          }
+        } else {
+          const int lo = g.wbit < g2.wbit ? g.wbit : g2.wbit, hi = g.wbit < g2.wbit ? g2.wbit : g.wbit;
+          const unsigned mlo = (1u << lo) - 1u, mhi = (1u << (hi - 1)) - 1u;   // masks on the compacted index
+          const int BA = 1 << g.wbit, BB = 1 << g2.wbit;
+#pragma unroll 2
+          for (int q = tid; q < S / 4; q += NT) {
+            const unsigned q1 = (((unsigned)q & ~mhi) << 1) | ((unsigned)q & mhi);   // zero at bit hi-1 ...
+            const int i00 = (int)(((q1 & ~mlo) << 1) | (q1 & mlo));                  // ... then at bit lo
+            double2 x00 = s_state[i00], xA = s_state[i00 | BA], xB = s_state[i00 | BB], xAB = s_state[i00 | BA | BB];
+            apply_pair(g, i00, x00, xA);
+            apply_pair(g, i00 | BB, xB, xAB);
+            apply_pair(g2, i00, x00, xB);
+            apply_pair(g2, i00 | BA, xA, xAB);
+            if (want2) {
+              metric_acc<UC>(x00, __ldg(tgt + i00), ra, rb);
+              metric_acc<UC>(xA, __ldg(tgt + (i00 | BA)), ra, rb);
+              metric_acc<UC>(xB, __ldg(tgt + (i00 | BB)), ra, rb);
+              metric_acc<UC>(xAB, __ldg(tgt + (i00 | BA | BB)), ra, rb);
+            }
+            if (reset2) {
+              x00 = reset_amp(UC, b.n_qubits, i00); xA = reset_amp(UC, b.n_qubits, i00 | BA);
+              xB = reset_amp(UC, b.n_qubits, i00 | BB); xAB = reset_amp(UC, b.n_qubits, i00 | BA | BB);
+            }
+            s_state[i00] = x00; s_state[i00 | BA] = xA; s_state[i00 | BB] = xB; s_state[i00 | BA | BB] = xAB;
+          }
+        }
+        if (want2) block_sums(ra, rb);
+        __syncthreads();
+        if (tid == 0) {
+          double xa = 0.0, xb = 0.0;
+          if (want2) read_sums(xa, xb);
+          finalize0(t + 1, want2, xa, xb);
+        }
+        if (reset2) e.meta = make_uint4(0, 0, 0, 0);
+        par ^= 1;
+        si += 2;
+        continue;
+      }
+
+      // ---- single-step pass
       const unsigned lowmask = (1u << g.wbit) - 1u;
       const int wb = 1 << g.wbit;
+      const int kind = g.kind;
       double ra = 0.0, rb = 0.0;
       if (want_metric) {
 #pragma unroll 1
@@ -681,12 +811,7 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
             if (kind != K_NONE || reset) { s_state[i0[u]] = x0[u]; s_state[i0[u] | wb] = x1[u]; }
           }
         }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          ra += __shfl_xor_sync(0xffffffffu, ra, off);
-          rb += __shfl_xor_sync(0xffffffffu, rb, off);
-        }
-        if ((tid & 31) == 0) s_wred[par][tid >> 5] = make_double2(ra, rb);
+        block_sums(ra, rb);
       } else if (kind != K_NONE) {                            // light path: touch only what changes
 #pragma unroll 4
         for (int j = 0; j < PPT; ++j) {
@@ -706,44 +831,14 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         }
       }
       __syncthreads();
-      if (tid == 0) {                                         // env.py:106-114,133-135 + Monitor + records
+      if (tid == 0) {
         double xa = 0.0, xb = 0.0;
-        if (want_metric) {
-#pragma unroll
-          for (int wv = 0; wv < NT / 32; ++wv) { xa += s_wred[par][wv].x; xb += s_wred[par][wv].y; }
-        }
-        const StepOut o = finalize_step<UC>(b, e, xa, xb, want_metric);
-        if (out.reward) out.reward[(long)t * N + env] = o.reward;
-        if (out.metric) out.metric[(long)t * N + env] = o.metric;
-        if (out.cost) out.cost[(long)t * N + env] = o.cost;
-        if (out.depth) out.depth[(long)t * N + env] = e.depth;
-        if (out.terminated) out.terminated[(long)t * N + env] = e.term;
-        if (out.truncated) out.truncated[(long)t * N + env] = e.trunc;
-        if (out.status) out.status[(long)t * N + env] = (int8_t)e.status;
-        if (t == T - 1) {
-          b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
-          b.depth[env] = e.depth; b.operations[env] = e.ops; b.used_wires[env] = e.used_cnt;
-          b.terminated[env] = e.term; b.truncated[env] = e.trunc; b.status[env] = (int8_t)e.status;
-        }
-        if (stats) {
-          if (e.status != QCD_ST_OK) atomicAdd(stats + QCD_STAT_BAD_ACTIONS, 1.0);
-          else atomicAdd(stats + QCD_STAT_STEPS, 1.0);
-        }
-        if (done) {
-          if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
-          if (stats) {
-            atomicAdd(stats + QCD_STAT_EPISODES, 1.0);
-            if (b.ep_return) { atomicAdd(stats + QCD_STAT_SUM_R, e.ep_ret); atomicAdd(stats + QCD_STAT_SUM_L, (double)e.ep_len); }
-            atomicAdd(stats + QCD_STAT_SUM_D, (double)e.depth); atomicAdd(stats + QCD_STAT_SUM_O, (double)e.ops);
-            atomicAdd(stats + QCD_STAT_SUM_Q, (double)e.used_cnt);
-            atomicAdd(stats + QCD_STAT_SUM_M, o.metric); atomicAdd(stats + QCD_STAT_SUM_C, o.cost);
-            atomicAdd(stats + (e.trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE), 1.0);
-          }
-          if (autoreset) { e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0; }
-        }
+        if (want_metric) read_sums(xa, xb);
+        finalize0(t, want_metric, xa, xb);
       }
       if (reset) e.meta = make_uint4(0, 0, 0, 0);             // env.py:117-121, every thread's copy
       par ^= 1;
+      si += 1;
     }
     __syncthreads();                                          // table may be overwritten by the next chunk
   }
