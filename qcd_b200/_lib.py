@@ -64,10 +64,16 @@ def load_library(path: str | None = None) -> C.CDLL:
   if _lib is not None and path is None:
     return _lib
   p = path or LIB_PATH
+  if not os.path.exists(p) and path is None:
+    try:                                  # a fresh checkout: compile the real thing (needs nvcc) ...
+      from .build import build_library
+      build_library()
+    except Exception as exc:              # ... and fail loudly otherwise: there is nothing to fall back to
+      raise RuntimeError(
+          f"{p} is missing and could not be built ({exc}). Build it with `python -m qcd_b200.build` "
+          "(or __graft_entry__.build()). qcd_b200 has no CPU fallback.") from exc
   if not os.path.exists(p):
-    raise RuntimeError(
-        f"{p} is missing: build it with `python -m qcd_b200.build` (or __graft_entry__.build()). "
-        "qcd_b200 has no CPU fallback.")
+    raise RuntimeError(f"{p} is missing. qcd_b200 has no CPU fallback.")
   lib = C.CDLL(p)
   lib.qcd_abi_version.restype = C.c_int
   lib.qcd_abi_version.argtypes = []
