@@ -405,7 +405,11 @@ def run_native(args):
 
   # ---- end to end through the public API with HOST buffers (step workloads only)
   e2e = None
-  if mode == 'step':
+  host_obs_bytes = N * 2 * S * 4 if obs_mode != 'none' and not args.e2e_no_obs else 0
+  if mode == 'step' and (host_obs_bytes > 8e9 or args.e2e_steps <= 0):
+    e2e = {"value": None, "unit": UNIT, "skipped": "pinned host observation buffer would be "
+           f"{host_obs_bytes / 1e9:.0f} GB" if host_obs_bytes > 8e9 else "--e2e-steps 0"}
+  elif mode == 'step':
     venv = CircuitDesignerVectorEnv(N, eta, delta, objective, target=target, device=dev, obs_mode=obs_mode)
     venv.reset()
     Ke = max(3, min(K, args.e2e_steps))
@@ -446,7 +450,9 @@ def run_native(args):
   tpath = os.path.join(ROOT, "profiles", "traffic.json")
   if os.path.exists(tpath):
     try:
-      traffic = json.load(open(tpath)).get(args.workload)
+      rec = json.load(open(tpath)).get(args.workload)
+      if isinstance(rec, dict):
+        traffic = int(rec["bytes"] * (N / rec["envs"]))
     except Exception:
       traffic = None
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
