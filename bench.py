@@ -43,6 +43,11 @@ WORKLOADS = {
     'uc-toffoli': ('UC-toffoli', 3, 30, 65536, 'step'),           # configs[2]
     'sp-random12': ('SP-random', 12, 36, 16384, 'step'),          # configs[3] shape (N scaled to --envs)
     'uc-random6': ('UC-random', 6, 24, 16384, 'step'),            # configs[4] shape, step kernel
+    'sp-ghz3': ('SP-ghz3', 3, 15, 1048576, 'step'),
+    'sp-random1': ('SP-random', 1, 6, 1048576, 'step'),
+    'sp-random4': ('SP-random', 4, 12, 1048576, 'step'),
+    'uc-hadamard1': ('UC-hadamard', 1, 9, 1048576, 'step'),
+    'uc-hadamard2': ('UC-hadamard', 2, 9, 1048576, 'step'),
     'sp-random6': ('SP-random', 6, 18, 524288, 'step'),
     'sp-random7': ('SP-random', 7, 21, 524288, 'step'),
     'sp-random8': ('SP-random', 8, 24, 262144, 'step'),

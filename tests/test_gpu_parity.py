@@ -191,3 +191,26 @@ def test_large_batch_indexing(cuda_device):
   np.testing.assert_allclose(gpu.reward[-M:].cpu().numpy(), ora.reward, atol=TOL, rtol=0)
   np.testing.assert_array_equal(gpu.depth[-M:].cpu().numpy(), ora.depth)
   assert gpu.stats[10].item() == N * T
+
+
+@pytest.mark.parametrize("objective,eta,delta,N", [('SP-random', 9, 27, 9), ('UC-random', 5, 20, 5), ('SP-ghz5', 5, 20, 70)])
+def test_replay_long_tape_crosses_decode_chunks(cuda_device, objective, eta, delta, N):
+  """T = 300 > 256: the CTA replay kernel decodes the tape in chunks of 256 steps (fusion never spans a
+  chunk boundary); the warp replay kernel prefetches the next action every step."""
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(21)
+  T = 300
+  target = make_target(objective, eta, seed=9)
+  a = EnvBatch(N, eta, delta, objective, target)
+  b = EnvBatch(N, eta, delta, objective, target)
+  tape = torch.as_tensor(uniform_box_tape(rng, eta, T, N), device=cuda_device)
+  rec = {'reward': torch.zeros((T, N), dtype=torch.float64, device=cuda_device),
+         'depth': torch.zeros((T, N), dtype=torch.int32, device=cuda_device)}
+  b.replay(tape, rec)
+  for t in range(T):
+    a.step(tape[t])
+    assert torch.equal(rec['depth'][t], a.depth), t
+    assert torch.allclose(rec['reward'][t], a.reward, atol=1e-13, rtol=0), t
+  assert torch.equal(a.state, b.state) and torch.equal(a.meta, b.meta) and torch.equal(a.obs, b.obs)
+  assert torch.equal(a.ep_length, b.ep_length)
+  assert torch.allclose(a.stats, b.stats, rtol=1e-12, atol=1e-9)
