@@ -41,26 +41,38 @@
 
 namespace qcd {
 
+// ---- compile-time tuning knobs (defaults = the values measured best on B200, profiles/r01_summary.md;
+// override with QCD_NVCC_EXTRA="-DNAME=value" python -m qcd_b200.build)
 #ifndef QCD_REG_STEP_MAX_LOG2S
-#define QCD_REG_STEP_MAX_LOG2S 7     // S <= 128: warp-autonomous step kernel; above: pair-streaming
+#define QCD_REG_STEP_MAX_LOG2S 7        // S <= 128: warp-autonomous step kernel; above: pair-streaming
 #endif
 #ifndef QCD_STEP_IMPL
-#define QCD_STEP_IMPL 2                // small-S step path: 0 pair-streaming, 2 warp-autonomous
+#define QCD_STEP_IMPL 2                 // small-S step path: 0 pair-streaming, 2 warp-autonomous
 #endif
+// warp-autonomous step kernel
 #ifndef QCD_WARP_STEP_WARPS
-#define QCD_WARP_STEP_WARPS 1           // warps per CTA (each warp is autonomous; 1 balances best across 148 SMs)
+#define QCD_WARP_STEP_WARPS 1           // warps per CTA (each warp is autonomous; 1 balances best over 148 SMs)
 #endif
 #ifndef QCD_WARP_STEP_MINB
-#define QCD_WARP_STEP_MINB 16          // min CTAs per SM for __launch_bounds__ (caps registers at 128)
+#define QCD_WARP_STEP_MINB 16           // min CTAs per SM for __launch_bounds__ (caps registers at 128)
 #endif
+#ifndef QCD_WARP_STEP_TILE
+#define QCD_WARP_STEP_TILE 32           // envs per warp tile (0 = 8 KiB of state per tile, clamped to 8..32)
+#endif
+#ifndef QCD_WARP_STEP_STAGE
+#define QCD_WARP_STEP_STAGE 0           // 1: stage the tile in smem with cp.async.bulk (TMA) when it fits 16 KiB
+#endif                                  //    (measured slower than the register prefetch, kept as an option)
 #ifndef QCD_WARP_PF_V1
-#define QCD_WARP_PF_V1 8                // rounds of state prefetched in registers when V == 1
+#define QCD_WARP_PF_V1 8                // rounds of state prefetched in registers at V = 1 amplitude per lane
 #endif
 #ifndef QCD_WARP_PF_V2
-#define QCD_WARP_PF_V2 2
+#define QCD_WARP_PF_V2 2                // ... at V = 2
 #endif
 #ifndef QCD_WARP_PF_V4
-#define QCD_WARP_PF_V4 2
+#define QCD_WARP_PF_V4 2                // ... at V = 3..4
+#endif
+#ifndef QCD_WARP_UNROLL_CHUNKS
+#define QCD_WARP_UNROLL_CHUNKS 0        // 1: fully unroll the chunk loop (measured slower: I-cache)
 #endif
 #ifndef QCD_WARP_BRANCHLESS
 #define QCD_WARP_BRANCHLESS 1           // branch-free round body (select instead of switch) ...
@@ -69,26 +81,25 @@ namespace qcd {
 #define QCD_WARP_BRANCHLESS_MAX_V 2     // ... for at most this many amplitudes per lane (S <= 64)
 #endif
 #ifndef QCD_WARP_LOG2L_S32
-#define QCD_WARP_LOG2L_S32 5            // log2(lanes per env) of the warp kernels at S = 32
+#define QCD_WARP_LOG2L_S32 5            // log2(lanes per env) of the warp kernels at S = 32 (fewer: slower)
 #endif
 #ifndef QCD_WARP_LOG2L_S64
 #define QCD_WARP_LOG2L_S64 5            // ... at S = 64
 #endif
+// pair-streaming step kernel
 #ifndef QCD_PAIR_SMALL_MAX_S
-#define QCD_PAIR_SMALL_MAX_S 4096
+#define QCD_PAIR_SMALL_MAX_S 4096       // up to this S the CTA has QCD_PAIR_SMALL_THREADS threads
 #endif
 #ifndef QCD_PAIR_SMALL_THREADS
-#define QCD_PAIR_SMALL_THREADS 32    // pair-streaming step: one warp (= one env) per CTA measured best at every S
+#define QCD_PAIR_SMALL_THREADS 32       // one warp (= one env) per CTA measured best at every S
 #endif
 #ifndef QCD_PAIR_L2_PREFETCH
-#define QCD_PAIR_L2_PREFETCH 1
+#define QCD_PAIR_L2_PREFETCH 1          // pull the env's lines into L2 while lane 0 decodes ...
 #endif
 #ifndef QCD_PAIR_L2_PREFETCH_MAX_S
-#define QCD_PAIR_L2_PREFETCH_MAX_S 1024
+#define QCD_PAIR_L2_PREFETCH_MAX_S 1024 // ... for S up to this (hurts at 32-64 KiB per env)
 #endif
-#ifndef QCD_PDL_EARLY
-#define QCD_PDL_EARLY 0
-#endif
+// replay kernels
 #ifndef QCD_REPLAY_WARP
 #define QCD_REPLAY_WARP 1               // replay for S <= 256: warp-autonomous, tile resident in smem
 #endif
@@ -99,26 +110,16 @@ namespace qcd {
 #define QCD_WARP_REPLAY_MINB 16
 #endif
 #ifndef QCD_WARP_REPLAY_TILE_BYTES
-#define QCD_WARP_REPLAY_TILE_BYTES 8192
+#define QCD_WARP_REPLAY_TILE_BYTES 8192 // state bytes per warp tile (ghz5: 16 envs)
+#endif
+#ifndef QCD_REPLAY_CTA
+#define QCD_REPLAY_CTA 1                // replay for S >= 512: CTA per env with decode-ahead (0: first version)
 #endif
 #ifndef QCD_REPLAY_FUSE
 #define QCD_REPLAY_FUSE 1               // replay_cta_kernel: two consecutive gates per sweep over the state
 #endif
 #ifndef QCD_REPLAY_MINB
-#define QCD_REPLAY_MINB 2                // CTAs/SM the 64-KiB replay kernel is compiled for (3 fit in smem but spill)
-#endif
-#ifndef QCD_REPLAY_CTA
-#define QCD_REPLAY_CTA 1                // replay for S >= 512: CTA per env with decode-ahead (0: first version)
-#endif
-#ifndef QCD_WARP_UNROLL_CHUNKS
-#define QCD_WARP_UNROLL_CHUNKS 0
-#endif
-#ifndef QCD_WARP_STEP_TILE
-#define QCD_WARP_STEP_TILE 32          // envs per warp tile (0 = 8 KiB of state per tile, clamped to 8..32)
-#endif
-#ifndef QCD_WARP_STEP_STAGE
-#define QCD_WARP_STEP_STAGE 0         // 1: stage the tile in smem with cp.async.bulk (TMA) when it fits 16 KiB
-                                     // (measured slower than the register prefetch on B200, kept as an option)
+#define QCD_REPLAY_MINB 2               // CTAs/SM the 64-KiB replay kernel is compiled for (3 fit in smem but spill)
 #endif
 
 constexpr int K_NONE = 0, K_P = 1, K_RX = 2, K_CP = 3, K_CX = 4;
@@ -195,17 +196,18 @@ __device__ __forceinline__ GateKind decode_kind(const int n_qubits, double a0, d
   }
   if (k.kind == K_P || k.kind == K_CP || k.kind == K_RX) {
     const double arg = (k.kind == K_RX) ? a3 / 2 : a3;         // RXGate: cos/sin(theta/2)
-#if defined(QCD_EXP_NOSINCOS)
-    k.cr = 1.0 - arg * arg * 0.5; k.sr = arg;   // EXPERIMENT ONLY (wrong numerics): decode-latency probe
-#else
     sincos(arg, &k.sr, &k.cr);
-#endif
   }
   return k;
 }
 
+__device__ __forceinline__ double depth_cost(const qcd_batch_t& b, const int depth) {
+  return fmax(0.0, (double)depth - b.depth_free) / b.cost_denom;                       // env.py:112
+}
+
 // QuantumCircuit.depth/count_ops/idle_wires bookkeeping (env.py:74,77,86) + truncation (env.py:129)
 // + cost (env.py:112): the sequential part (integer only, apart from the cost division).
+template <bool WITH_COST = true>
 __device__ __forceinline__ void book_gate(const qcd_batch_t& b, const int status, const int kind, const int w,
                                           const int c, const bool term, EnvCtl& e) {
   uint32_t ops = e.meta.w & 0xffffu, used = e.meta.w >> 16;
@@ -226,7 +228,7 @@ __device__ __forceinline__ void book_gate(const qcd_batch_t& b, const int status
   e.status = status; e.term = term;
   e.trunc = (status == QCD_ST_OK) &&
             (depth >= b.max_depth || (int)ops >= b.max_depth * b.n_qubits * 2);        // env.py:129
-  e.cost_raw = fmax(0.0, (double)depth - b.depth_free) / b.cost_denom;                 // env.py:112
+  if (WITH_COST) e.cost_raw = depth_cost(b, depth);                                    // env.py:112
 }
 
 __device__ __forceinline__ void decode_action(const qcd_batch_t& b, double a0, double a1, double a2,
@@ -651,6 +653,7 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
     // thread 0: env.py:106-114,133-135 + Monitor + records of step t (uses e as booked for step t)
     auto finalize0 = [&](const int t, const bool want_metric, const double xa, const double xb) {
       const bool done = (e.status == QCD_ST_OK) && (e.term || e.trunc);
+      e.cost_raw = depth_cost(b, e.depth);                    // the one division of the step
       const StepOut o = finalize_step<UC>(b, e, xa, xb, want_metric);
       if (out.reward) out.reward[(long)t * N + env] = o.reward;
       if (out.metric) out.metric[(long)t * N + env] = o.metric;
@@ -707,7 +710,7 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       int status, w, c;
       bool term;
       unpack(s_tab[si], g, status, term, w, c);
-      book_gate(b, status, g.kind, w, c, term, e);            // identical in every thread
+      book_gate<false>(b, status, g.kind, w, c, term, e);     // identical in every thread (cost: thread 0)
       const bool done = (status == QCD_ST_OK) && (e.term || e.trunc);
       const bool reset = done && autoreset;
       const bool want_metric = metric_every_step || done || t == T - 1;
@@ -721,7 +724,7 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         int status2, w2, c2;
         bool term2;
         unpack(s_tab[si + 1], g2, status2, term2, w2, c2);
-        book_gate(b, status2, g2.kind, w2, c2, term2, e);
+        book_gate<false>(b, status2, g2.kind, w2, c2, term2, e);
         const bool done2 = (status2 == QCD_ST_OK) && (e.term || e.trunc);
         const bool reset2 = done2 && autoreset;
         const bool want2 = metric_every_step || done2 || t + 1 == T - 1;
@@ -987,9 +990,6 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
     load_action(actions, act_f32, env, a0, a1, a2, a3);
     gk = decode_kind(b.n_qubits, a0, a1, a2, a3);
   }
-#if QCD_PDL_EARLY
-  pdl_launch_dependents();                        // the next step's grid may start its scalar phase now
-#endif
   pdl_wait();
   if (STAGE) {                                    // the tile goes in flight first
     if (lane == 0) {
@@ -1238,9 +1238,8 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   }
 
   // ---- finalize + scalar outputs + fused statistics
-#if !QCD_PDL_EARLY
   pdl_launch_dependents();                        // the next step's grid may start its scalar phase now
-#endif
+                                                  // (triggering at kernel entry measured 2 % slower)
   const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   phase3<UC, 32>(b, none, e, ctl, env, 0, 1, N, lane, mysum, ctl, stats_slice(b, tile));
   if (ctl) {
