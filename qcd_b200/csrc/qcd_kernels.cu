@@ -71,6 +71,9 @@ namespace qcd {
 #ifndef QCD_WARP_PF_V4
 #define QCD_WARP_PF_V4 2                // ... at V = 3..4
 #endif
+#ifndef QCD_WARP_CHUNK
+#define QCD_WARP_CHUNK 8                // rounds per metric-reduction chunk (power of two <= 32)
+#endif
 #ifndef QCD_WARP_UNROLL_CHUNKS
 #define QCD_WARP_UNROLL_CHUNKS 0        // 1: fully unroll the chunk loop (measured slower: I-cache)
 #endif
@@ -904,7 +907,7 @@ struct WarpCfg {
   static constexpr int V = S / L, LOG2V = LOG2S - LOG2L;
   static constexpr int G = 32 / L, LOG2G = 5 - LOG2L;       // envs per round
   static constexpr int R = TE / G;                         // rounds per tile
-  static constexpr int C = R < 8 ? R : 8;                  // rounds per reduction chunk
+  static constexpr int C = R < QCD_WARP_CHUNK ? R : QCD_WARP_CHUNK;   // rounds per reduction chunk
   static constexpr int PF0 = V == 1 ? QCD_WARP_PF_V1 : (V == 2 ? QCD_WARP_PF_V2 : (V <= 4 ? QCD_WARP_PF_V4 : 1));
   static constexpr int PF = STAGE ? 1 : (PF0 < C ? PF0 : C);   // rounds of state in flight in registers
   static constexpr int ROW = 36;                           // double2 slots per scratch row
