@@ -10,6 +10,7 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - calls are asynchronous on `stream`, never synchronise, never allocate, keep no global state;
  *   - return value: 0 ok, <0 invalid argument (QCD_E_*), >0 a cudaError_t from the launch;
+ *     a batch with n_envs == 0 is a valid no-op;
  *   - the `_host` variants take HOST pointers for actions/results and issue the copies on `stream`.
  *
  * Layouts (N = n_envs, eta = n_qubits, D = 2^eta, S = D for SP, D*D for UC):

@@ -1667,6 +1667,7 @@ extern "C" {
 int qcd_abi_version(void) { return QCD_ABI_VERSION; }
 
 int qcd_reset(const qcd_batch_t* b, const uint8_t* mask, void* stream) {
+  if (b && b->n_envs == 0) return 0;          // empty batch: nothing to do
   int rc = qcd::validate(b, false, nullptr, QCD_ACT_F64);
   if (rc) return rc;
   const int log2s = b->objective == QCD_OBJ_UC ? 2 * b->n_qubits : b->n_qubits;
@@ -1677,6 +1678,7 @@ int qcd_reset(const qcd_batch_t* b, const uint8_t* mask, void* stream) {
 }
 
 int qcd_step(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream) {
+  if (b && b->n_envs == 0) return 0;          // empty batch: nothing to do
   int rc = qcd::validate(b, true, actions, action_dtype);
   if (rc) return rc;
   const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1685,6 +1687,7 @@ int qcd_step(const qcd_batch_t* b, const void* actions, int action_dtype, void* 
 
 int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int32_t n_steps,
                const qcd_tape_out_t* out, void* stream) {
+  if (b && b->n_envs == 0) return 0;          // empty batch: nothing to do
   int rc = qcd::validate(b, true, actions, action_dtype);
   if (rc) return rc;
   if (n_steps < 1) return QCD_E_RANGE;
@@ -1697,6 +1700,7 @@ int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int3
 }
 
 int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream) {
+  if (b && b->n_envs == 0) return 0;          // empty batch: nothing to do
   int rc = qcd::validate(b, false, nullptr, QCD_ACT_F64);
   if (rc) return rc;
   if (!stats) return QCD_E_NULL;
@@ -1708,6 +1712,7 @@ int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream) {
 
 int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_dev, int action_dtype,
                   const qcd_host_out_t* out, void* stream) {
+  if (b && b->n_envs == 0) return 0;          // empty batch: nothing to do
   int rc = qcd::validate(b, true, actions_dev, action_dtype);
   if (rc) return rc;
   if (!actions_host || !out) return QCD_E_NULL;

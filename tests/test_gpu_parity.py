@@ -214,3 +214,37 @@ def test_replay_long_tape_crosses_decode_chunks(cuda_device, objective, eta, del
   assert torch.equal(a.state, b.state) and torch.equal(a.meta, b.meta) and torch.equal(a.obs, b.obs)
   assert torch.equal(a.ep_length, b.ep_length)
   assert torch.allclose(a.stats, b.stats, rtol=1e-12, atol=1e-9)
+
+
+def test_empty_batch_is_a_noop(cuda_device):
+  from qcd_b200.batch import EnvBatch
+  b = EnvBatch(0, 3, 15, 'SP-ghz3', make_target('SP-ghz3', 3))
+  b.step(torch.zeros((0, 4), dtype=torch.float32, device=cuda_device))
+  b.replay(torch.zeros((5, 0, 4), dtype=torch.float32, device=cuda_device))
+  b.reset(); b.reduce_stats()
+  torch.cuda.synchronize()
+  assert b.state.shape == (0, 8) and float(b.stats.sum()) == 0
+
+
+@pytest.mark.parametrize("objective,eta", [('SP-random', 2), ('UC-random', 2)])
+def test_maximum_depth_255_counter_boundary(cuda_device, objective, eta):
+  """max_depth = 255 is the largest the uint8 depth stack supports: episodes must truncate exactly
+  there (and reset), identically to the oracle, over several such episodes."""
+  rng = np.random.default_rng(3)
+  N, T, delta = 48, 900, 255
+  target = make_target(objective, eta, seed=1)
+  gpu, ora = _pair(N, eta, delta, objective, target, obs_mode='state')
+  tape = uniform_box_tape(rng, eta, T, N, no_terminate=True)
+  tape[..., 2] = tape[..., 1]                       # single-qubit gates only: depth grows by <= 1 per step
+  dev_tape = torch.as_tensor(tape, device=cuda_device)
+  seen = 0
+  for t in range(T):
+    gpu.step(dev_tape[t]); ora.step(tape[t])
+    if ora.truncated.any():
+      seen += int(ora.truncated.sum())
+      assert (ora.depth[ora.truncated.astype(bool)] == 255).all()
+      np.testing.assert_array_equal(gpu.truncated.cpu().numpy(), ora.truncated)
+      np.testing.assert_array_equal(gpu.depth.cpu().numpy(), ora.depth)
+      np.testing.assert_allclose(gpu.reward.cpu().numpy(), ora.reward, atol=TOL, rtol=0)
+  assert seen >= N
+  _cmp(gpu, ora, what="end")

@@ -55,3 +55,21 @@ def test_invalid_actions_leave_env_untouched():
   assert list(b.status) == [1, 1, 2, 2]
   np.testing.assert_array_equal(b.state, before); np.testing.assert_array_equal(b.meta, meta)
   assert not b.terminated.any() and not b.truncated.any() and (b.reward == 0).all()
+
+
+def test_c_oracle_depth_255_boundary_matches_einsum_oracle():
+  """uint8 depth counters of the batched layout: truncation at max_depth = 255 happens on the same
+  step as in the (unbounded-counter) einsum oracle."""
+  eta, delta = 1, 255
+  target = make_target('SP-random', eta, seed=2)
+  env = OracleCircuitDesigner(eta, delta, 'SP-random', target=target)
+  cb = OracleBatch(1, eta, delta, 'SP-random', target, autoreset=False)
+  env.reset()
+  a = np.array([1.0, 0.0, 0.0, 0.37], np.float32)
+  for t in range(255):
+    obs, r, term, trunc, info = env.step(a)
+    cb.step(a[None])
+    assert bool(cb.truncated[0]) == trunc == (t == 254)
+    assert cb.depth[0] == info['depth'] == t + 1
+  np.testing.assert_allclose(cb.reward[0], r, atol=1e-13)
+  assert info['cost'] == cb.cost[0] == (255 - 255 / 3) / (255 / 2 * 3)
