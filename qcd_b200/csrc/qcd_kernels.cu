@@ -595,6 +595,46 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
   }
 }
 
+// env.py:106-114,133-135 + Monitor + per-step records of ONE env, by its control thread (replay kernels).
+template <bool UC>
+__device__ __forceinline__ void finalize_and_emit(const qcd_batch_t& b, const qcd_tape_out_t& out, EnvCtl& e,
+                                                  const int t, const int T, const long N, const long env,
+                                                  const bool want_metric, const double xa, const double xb,
+                                                  double* stats) {
+  const bool autoreset = b.flags & QCD_F_AUTORESET;
+  const bool done = (e.status == QCD_ST_OK) && (e.term || e.trunc);
+  e.cost_raw = depth_cost(b, e.depth);
+  const StepOut o = finalize_step<UC>(b, e, xa, xb, want_metric);
+  if (out.reward) out.reward[(long)t * N + env] = o.reward;
+  if (out.metric) out.metric[(long)t * N + env] = o.metric;
+  if (out.cost) out.cost[(long)t * N + env] = o.cost;
+  if (out.depth) out.depth[(long)t * N + env] = e.depth;
+  if (out.terminated) out.terminated[(long)t * N + env] = e.term;
+  if (out.truncated) out.truncated[(long)t * N + env] = e.trunc;
+  if (out.status) out.status[(long)t * N + env] = (int8_t)e.status;
+  if (t == T - 1) {
+    b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
+    b.depth[env] = e.depth; b.operations[env] = e.ops; b.used_wires[env] = e.used_cnt;
+    b.terminated[env] = e.term; b.truncated[env] = e.trunc; b.status[env] = (int8_t)e.status;
+  }
+  if (stats) {
+    if (e.status != QCD_ST_OK) atomicAdd(stats + QCD_STAT_BAD_ACTIONS, 1.0);
+    else atomicAdd(stats + QCD_STAT_STEPS, 1.0);
+  }
+  if (done) {
+    if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
+    if (stats) {
+      atomicAdd(stats + QCD_STAT_EPISODES, 1.0);
+      if (b.ep_return) { atomicAdd(stats + QCD_STAT_SUM_R, e.ep_ret); atomicAdd(stats + QCD_STAT_SUM_L, (double)e.ep_len); }
+      atomicAdd(stats + QCD_STAT_SUM_D, (double)e.depth); atomicAdd(stats + QCD_STAT_SUM_O, (double)e.ops);
+      atomicAdd(stats + QCD_STAT_SUM_Q, (double)e.used_cnt);
+      atomicAdd(stats + QCD_STAT_SUM_M, o.metric); atomicAdd(stats + QCD_STAT_SUM_C, o.cost);
+      atomicAdd(stats + (e.trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE), 1.0);
+    }
+    if (autoreset) { e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2 for large states (S >= 512): one CTA per env, the state resident in shared memory for the whole
 // tape.  What made the first replay kernel slow was a per-step serial chain (one thread decoding an
@@ -655,37 +695,7 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
     const int nsteps = (T - t0) < NT ? (T - t0) : NT;
     // thread 0: env.py:106-114,133-135 + Monitor + records of step t (uses e as booked for step t)
     auto finalize0 = [&](const int t, const bool want_metric, const double xa, const double xb) {
-      const bool done = (e.status == QCD_ST_OK) && (e.term || e.trunc);
-      e.cost_raw = depth_cost(b, e.depth);                    // the one division of the step
-      const StepOut o = finalize_step<UC>(b, e, xa, xb, want_metric);
-      if (out.reward) out.reward[(long)t * N + env] = o.reward;
-      if (out.metric) out.metric[(long)t * N + env] = o.metric;
-      if (out.cost) out.cost[(long)t * N + env] = o.cost;
-      if (out.depth) out.depth[(long)t * N + env] = e.depth;
-      if (out.terminated) out.terminated[(long)t * N + env] = e.term;
-      if (out.truncated) out.truncated[(long)t * N + env] = e.trunc;
-      if (out.status) out.status[(long)t * N + env] = (int8_t)e.status;
-      if (t == T - 1) {
-        b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
-        b.depth[env] = e.depth; b.operations[env] = e.ops; b.used_wires[env] = e.used_cnt;
-        b.terminated[env] = e.term; b.truncated[env] = e.trunc; b.status[env] = (int8_t)e.status;
-      }
-      if (stats) {
-        if (e.status != QCD_ST_OK) atomicAdd(stats + QCD_STAT_BAD_ACTIONS, 1.0);
-        else atomicAdd(stats + QCD_STAT_STEPS, 1.0);
-      }
-      if (done) {
-        if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
-        if (stats) {
-          atomicAdd(stats + QCD_STAT_EPISODES, 1.0);
-          if (b.ep_return) { atomicAdd(stats + QCD_STAT_SUM_R, e.ep_ret); atomicAdd(stats + QCD_STAT_SUM_L, (double)e.ep_len); }
-          atomicAdd(stats + QCD_STAT_SUM_D, (double)e.depth); atomicAdd(stats + QCD_STAT_SUM_O, (double)e.ops);
-          atomicAdd(stats + QCD_STAT_SUM_Q, (double)e.used_cnt);
-          atomicAdd(stats + QCD_STAT_SUM_M, o.metric); atomicAdd(stats + QCD_STAT_SUM_C, o.cost);
-          atomicAdd(stats + (e.trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE), 1.0);
-        }
-        if (autoreset) { e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0; }
-      }
+      finalize_and_emit<UC>(b, out, e, t, T, N, env, want_metric, xa, xb, stats);
     };
     auto unpack = [&](const StepRec& r, GateRec& g, int& status, bool& term, int& w, int& c) {
       const int kind = r.pk & 7;
@@ -1542,6 +1552,7 @@ struct Launch {
       constexpr size_t smem = (size_t)S * sizeof(double2);
       constexpr int MINB = S >= 4096 ? QCD_REPLAY_MINB : (S >= 2048 ? 4 : 6);   // smem allows 3 CTAs of 64 KiB
       auto kern = replay_cta_kernel<LOG2S, UC, RNT, MINB>;
+      constexpr int BLOCK = RNT;
       static bool attr_done[64] = {false};
       int dev = 0;
       cudaGetDevice(&dev);
@@ -1550,7 +1561,7 @@ struct Launch {
         if (err != cudaSuccess) return (int)err;
         attr_done[dev & 63] = true;
       }
-      kern<<<(unsigned)b.n_envs, RNT, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
+      kern<<<(unsigned)b.n_envs, BLOCK, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
       return (int)cudaGetLastError();
     } else if constexpr (STAGED && S <= 256 && QCD_REPLAY_WARP) {
       if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
