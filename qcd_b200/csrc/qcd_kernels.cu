@@ -112,6 +112,9 @@ namespace qcd {
 #ifndef QCD_WARP_REPLAY_MINB
 #define QCD_WARP_REPLAY_MINB 16
 #endif
+#ifndef QCD_WARP_REPLAY_CHUNK
+#define QCD_WARP_REPLAY_CHUNK 8          // rounds per metric-reduction chunk of replay_warp_kernel
+#endif
 #ifndef QCD_WARP_REPLAY_TILE_BYTES
 #define QCD_WARP_REPLAY_TILE_BYTES 8192 // state bytes per warp tile (ghz5: 16 envs)
 #endif
@@ -917,7 +920,8 @@ struct WarpCfg {
   static constexpr int V = S / L, LOG2V = LOG2S - LOG2L;
   static constexpr int G = 32 / L, LOG2G = 5 - LOG2L;       // envs per round
   static constexpr int R = TE / G;                         // rounds per tile
-  static constexpr int C = R < QCD_WARP_CHUNK ? R : QCD_WARP_CHUNK;   // rounds per reduction chunk
+  static constexpr int CH = STAGE ? QCD_WARP_REPLAY_CHUNK : QCD_WARP_CHUNK;
+  static constexpr int C = R < CH ? R : CH;                // rounds per reduction chunk
   static constexpr int PF0 = V == 1 ? QCD_WARP_PF_V1 : (V == 2 ? QCD_WARP_PF_V2 : (V <= 4 ? QCD_WARP_PF_V4 : 1));
   static constexpr int PF = STAGE ? 1 : (PF0 < C ? PF0 : C);   // rounds of state in flight in registers
   static constexpr int ROW = 36;                           // double2 slots per scratch row
