@@ -124,6 +124,9 @@ namespace qcd {
 #ifndef QCD_REPLAY_FUSE
 #define QCD_REPLAY_FUSE 1               // replay_cta_kernel: two consecutive gates per sweep over the state
 #endif
+#ifndef QCD_REPLAY_SPECIALISE
+#define QCD_REPLAY_SPECIALISE 1         // light+light fused sweeps compiled per pair of gate kinds
+#endif
 #ifndef QCD_REPLAY_MINB
 #define QCD_REPLAY_MINB 2               // CTAs/SM the 64-KiB replay kernel is compiled for (3 fit in smem but spill)
 #endif
@@ -316,6 +319,77 @@ __device__ __forceinline__ void apply_pair(const GateRec& g, int i0, double2& a0
       if ((i0 >> g.cbit) & 1) { const double2 t = a0; a0 = a1; a1 = t; }
       break;
     default: break;
+  }
+}
+
+// apply_pair with the gate kind known at compile time (no switch in the inner loops of the replay sweeps)
+template <int KIND>
+__device__ __forceinline__ void apply_pair_k(const GateRec& g, const int i0, double2& a0, double2& a1) {
+  if (KIND == K_P) {
+    a1 = mul_phase(a1, g.cr, g.sr);
+  } else if (KIND == K_CP) {
+    if ((i0 >> g.cbit) & 1) a1 = mul_phase(a1, g.cr, g.sr);
+  } else if (KIND == K_RX) {
+    const double2 n0 = rot_rx(a0, a1, g.cr, g.sr), n1 = rot_rx(a1, a0, g.cr, g.sr);
+    a0 = n0; a1 = n1;
+  } else if (KIND == K_CX) {
+    if ((i0 >> g.cbit) & 1) { const double2 t = a0; a0 = a1; a1 = t; }
+  }
+}
+
+// One sweep over a state in shared memory applying gate A then gate B (both "light": no metric, no
+// reset) to the 4 amplitudes closed under the two wire bits — or to the pair when the wires coincide.
+template <int KA, int KB>
+__device__ __forceinline__ void sweep_two_gates(double2* __restrict__ st, const int S, const int tid, const int nt,
+                                                const GateRec& gA, const GateRec& gB) {
+  if (gA.wbit == gB.wbit) {
+    const unsigned lowmask = (1u << gA.wbit) - 1u;
+    const int wb = 1 << gA.wbit;
+#pragma unroll 2
+    for (int k = tid; k < S / 2; k += nt) {
+      const int i0 = (int)((((unsigned)k & ~lowmask) << 1) | ((unsigned)k & lowmask));
+      double2 x0 = st[i0], x1 = st[i0 | wb];
+      apply_pair_k<KA>(gA, i0, x0, x1);
+      apply_pair_k<KB>(gB, i0, x0, x1);
+      st[i0] = x0; st[i0 | wb] = x1;
+    }
+  } else {
+    const int lo = gA.wbit < gB.wbit ? gA.wbit : gB.wbit, hi = gA.wbit < gB.wbit ? gB.wbit : gA.wbit;
+    const unsigned mlo = (1u << lo) - 1u, mhi = (1u << (hi - 1)) - 1u;
+    const int BA = 1 << gA.wbit, BB = 1 << gB.wbit;
+#pragma unroll 2
+    for (int q = tid; q < S / 4; q += nt) {
+      const unsigned q1 = (((unsigned)q & ~mhi) << 1) | ((unsigned)q & mhi);
+      const int i00 = (int)(((q1 & ~mlo) << 1) | (q1 & mlo));
+      double2 x00 = st[i00], xA = st[i00 | BA], xB = st[i00 | BB], xAB = st[i00 | BA | BB];
+      apply_pair_k<KA>(gA, i00, x00, xA);
+      apply_pair_k<KA>(gA, i00 | BB, xB, xAB);
+      apply_pair_k<KB>(gB, i00, x00, xB);
+      apply_pair_k<KB>(gB, i00 | BA, xA, xAB);
+      st[i00] = x00; st[i00 | BA] = xA; st[i00 | BB] = xB; st[i00 | BA | BB] = xAB;
+    }
+  }
+}
+
+template <int KA>
+__device__ __forceinline__ void sweep_two_gates_b(double2* st, const int S, const int tid, const int nt,
+                                                  const GateRec& gA, const GateRec& gB) {
+  switch (gB.kind) {
+    case K_P:  sweep_two_gates<KA, K_P>(st, S, tid, nt, gA, gB); break;
+    case K_RX: sweep_two_gates<KA, K_RX>(st, S, tid, nt, gA, gB); break;
+    case K_CP: sweep_two_gates<KA, K_CP>(st, S, tid, nt, gA, gB); break;
+    default:   sweep_two_gates<KA, K_CX>(st, S, tid, nt, gA, gB); break;
+  }
+}
+
+// both kinds in {P, RX, CP, CX}
+__device__ __forceinline__ void sweep_two_gates_dispatch(double2* st, const int S, const int tid, const int nt,
+                                                         const GateRec& gA, const GateRec& gB) {
+  switch (gA.kind) {
+    case K_P:  sweep_two_gates_b<K_P>(st, S, tid, nt, gA, gB); break;
+    case K_RX: sweep_two_gates_b<K_RX>(st, S, tid, nt, gA, gB); break;
+    case K_CP: sweep_two_gates_b<K_CP>(st, S, tid, nt, gA, gB); break;
+    default:   sweep_two_gates_b<K_CX>(st, S, tid, nt, gA, gB); break;
   }
 }
 
@@ -745,7 +819,9 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         const bool reset2 = done2 && autoreset;
         const bool want2 = metric_every_step || done2 || t + 1 == T - 1;
         double ra = 0.0, rb = 0.0;
-        if (g.kind == K_NONE || g2.kind == K_NONE || g.wbit == g2.wbit) {
+        if (QCD_REPLAY_SPECIALISE && !want2 && !reset2 && g.kind != K_NONE && g2.kind != K_NONE) {
+          sweep_two_gates_dispatch(s_state, S, tid, NT, g, g2);   // light + light: kinds at compile time
+        } else if (g.kind == K_NONE || g2.kind == K_NONE || g.wbit == g2.wbit) {
           const int wbit = (g.kind != K_NONE) ? g.wbit : g2.wbit;
           const unsigned lowmask = (1u << wbit) - 1u;
           const int wb = 1 << wbit;
