@@ -376,6 +376,34 @@ def run_native(args):
   env_steps = N * K * steps_per_launch * world
   value = env_steps / (elapsed_ms * 1e-3)
 
+  # ---- a device-resident loop as an RL trainer would run it: a (stand-in) policy writes new actions on the
+  # GPU every step (torch.rand + affine map to the Box bounds, 3 small torch kernels), then the env steps;
+  # no graph, no host data.  Sits between `value` (tape replayed from a graph) and `e2e` (host buffers).
+  device_loop = None
+  if mode == 'step' and not args.no_sweep:
+    lowv = torch.tensor([0.0, 0.0, 0.0, -np.pi], device=dev, dtype=torch.float32)
+    span = torch.tensor([3 - 1e-5, eta - 1e-5, eta - 1e-5, 2 * np.pi], device=dev, dtype=torch.float32)
+    act = torch.empty((N, 4), device=dev, dtype=torch.float32)
+    Kd = min(K, 500)
+    with torch.cuda.stream(stream):
+      for i in range(10):
+        torch.rand((N, 4), out=act); act.mul_(span).add_(lowv); batches[i % R].step(act)
+      stream.synchronize()
+      if world > 1:
+        dist.barrier()
+      d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      d0.record(stream)
+      for i in range(Kd):
+        torch.rand((N, 4), out=act); act.mul_(span).add_(lowv); batches[i % R].step(act)
+      d1.record(stream)
+      stream.synchronize()
+    td = torch.tensor([d0.elapsed_time(d1)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    device_loop = {"value": N * Kd * world / (float(td.item()) * 1e-3), "unit": UNIT, "steps": Kd,
+                   "ms_per_step": float(td.item()) / Kd,
+                   "what": "torch.rand policy stand-in (3 torch kernels) + qcd_step per iteration, python-launched"}
+
   # ---- secondary point: the same kernel at 1 Mi envs per GPU (steady state, launch ramp amortised)
   sweep = None
   if mode == 'step' and not args.no_sweep and args.envs == 0 and S <= 64:
@@ -491,7 +519,7 @@ def run_native(args):
                  "cuda_graph": graph is not None, "graph_len": G if graph is not None else 0,
                  "steps_per_launch": steps_per_launch, "parallelism": f"env-sharded x{world}, stats all-reduce only"},
       "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu,
-      "episode_stats": summarize(stats[:qlib.STATS_LEN]), "sweep": sweep,
+      "episode_stats": summarize(stats[:qlib.STATS_LEN]), "sweep": sweep, "device_loop": device_loop,
   }
   print(json.dumps(line), flush=True)
   if world > 1:
