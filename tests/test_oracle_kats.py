@@ -93,3 +93,40 @@ def test_dense_reward_deltas_and_no_punish():
   total = 0
   for a in seq: total += env.step(a)[1]
   np.testing.assert_allclose(total, 1.0, atol=1e-14)      # telescoping sum of metric deltas
+
+
+def _dense(kind, qargs, theta, n):
+  """Full 2^n x 2^n matrix of one gate built WITHOUT the einsum core: explicit sum over basis states
+  with qiskit's documented little-endian convention (qubit k = bit k of the basis index; the gate's
+  own matrix is indexed with qargs[0] as its least-significant bit)."""
+  g = gate_matrix(kind, theta)
+  dim = 2 ** n
+  full = np.zeros((dim, dim), complex)
+  for col in range(dim):
+    sub_in = sum(((col >> q) & 1) << k for k, q in enumerate(qargs))
+    rest = col & ~sum(1 << q for q in qargs)
+    for sub_out in range(2 ** len(qargs)):
+      row = rest | sum(((sub_out >> k) & 1) << q for k, q in enumerate(qargs))
+      full[row, col] += g[sub_out, sub_in]
+  return full
+
+
+def test_einsum_core_equals_dense_little_endian_products():
+  from oracle.qcd_oracle import simulate_statevector
+  rng = np.random.default_rng(12)
+  for n in (1, 2, 3, 4):
+    ops = []
+    for _ in range(12):
+      kind = ['p', 'rx', 'cp', 'cx'][rng.integers(4)]
+      w = int(rng.integers(n))
+      if kind in ('cp', 'cx'):
+        if n == 1: continue
+        c = int((w + 1 + rng.integers(n - 1)) % n)
+        ops.append((kind, [c, w], float(rng.uniform(-PI, PI)) if kind == 'cp' else None))
+      else:
+        ops.append((kind, [w], float(rng.uniform(-PI, PI))))
+    U = np.eye(2 ** n, dtype=complex)
+    for kind, qargs, theta in ops:
+      U = _dense(kind, qargs, theta, n) @ U                      # left multiplication, circuit order
+    np.testing.assert_allclose(simulate_operator(ops, n), U, atol=1e-14)
+    np.testing.assert_allclose(simulate_statevector(ops, n), U[:, 0], atol=1e-14)
