@@ -42,3 +42,29 @@ def test_native_arm_needs_cuda():
     pytest.skip("CUDA present")
   res = _run("--steps", "3", "--warmup", "3", "--no-cpu")
   assert res.returncode != 0 and "no CPU fallback" in (res.stderr + res.stdout)
+
+
+@pytest.mark.gpu
+def test_native_arm_json_line_on_gpu(cuda_device):
+  """The default workload with a short run: ONE JSON line carrying the contract's keys, a measured
+  roofline against MEASURED_PEAKS.json, the CPU baseline, the end-to-end number and sane clocks."""
+  res = _run("--steps", "40", "--warmup", "5", "--cpu-seconds", "1", "--no-sweep", "--e2e-steps", "10", timeout=600)
+  assert res.returncode == 0, res.stderr[-2000:]
+  lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+    assert key in d, key
+  assert d["n_gpus"] == 1 and d["steps"] == 40 and d["gpu_launches"] == 40 and d["scaling"] == "weak"
+  assert d["vs_baseline"] is None and d["data"] == "synthetic" and "SP-ghz5" in d["config"]["workload"]
+  assert "model" not in d["config"] and d["config"]["cuda_graph"] is True
+  r = d["roofline"]
+  assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+  assert 0.2 < r["frac"] < 1.3 and r["traffic"] is None or r["traffic"] > 0
+  assert d["value"] > 1e9 and abs(d["value"] - 65536 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+  e = d["e2e"]
+  assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 65536 * 16 and e["d2h_bytes_per_step"] > 65536 * 10
+  c = d["cpu_baseline"]
+  assert c["kind"] == "port" and c["cores"] == 1 and 0 < c["value"] < 1e6
+  assert d["clocks"]["sm_max_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
