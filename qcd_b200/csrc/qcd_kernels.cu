@@ -96,6 +96,12 @@ namespace qcd {
 #ifndef QCD_PAIR_SMALL_THREADS
 #define QCD_PAIR_SMALL_THREADS 32       // one warp (= one env) per CTA measured best at every S
 #endif
+#ifndef QCD_PAIR_NARROW_MAX_S
+#define QCD_PAIR_NARROW_MAX_S 256       // pair-streaming step: for S up to this, only QCD_PAIR_NARROW_L lanes per env
+#endif
+#ifndef QCD_PAIR_NARROW_L
+#define QCD_PAIR_NARROW_L 8             // (several envs per warp => several decode lanes busy)
+#endif
 #ifndef QCD_PAIR_L2_PREFETCH
 #define QCD_PAIR_L2_PREFETCH 1          // pull the env's lines into L2 while lane 0 decodes ...
 #endif
@@ -1619,7 +1625,7 @@ struct Launch {
   static constexpr int S = 1 << LOG2S;
   // step: <= one warp per env, streaming.  replay: a whole CTA per env once the state is >= 32 KiB.
   static constexpr int NT = STAGED ? (S >= 2048 ? 256 : 128) : (S <= QCD_PAIR_SMALL_MAX_S ? QCD_PAIR_SMALL_THREADS : 256);
-  static constexpr int L = (STAGED && S >= 2048) ? NT : clampi(S / 4, 1, 32);
+  static constexpr int L = (STAGED && S >= 2048) ? NT : clampi(S / 4, 1, (!STAGED && S <= QCD_PAIR_NARROW_MAX_S) ? QCD_PAIR_NARROW_L : 32);
   static constexpr int LOG2L = ilog2(L);
   static constexpr int E = NT / L;
   static constexpr size_t SMEM = STAGED ? (size_t)E * S * sizeof(double2) : 0;
