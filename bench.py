@@ -494,8 +494,11 @@ def run_native(args):
                   ("replay_cta_kernel" if S >= 512 else "qcd_kernel(staged replay)"),
                   int(np.log2(S)), "UC" if 'UC' in objective else "SP"),
               "algorithmic_bytes_per_env_step": bytes_step_env, "launch_us": launch_ms * 1e3,
-              "note": "algorithmic bytes count a full state write; the kernels skip stores of amplitudes a "
-                      "gate leaves untouched (P/CP/CX/Terminate), so frac can read slightly above 1"}
+              "note": ("algorithmic bytes count a full state write; the kernels skip stores of amplitudes a "
+                       "gate leaves untouched (P/CP/CX/Terminate), so frac can read slightly above 1") if mode == 'step'
+              else ("replay keeps the state in shared memory for the whole tape: HBM traffic is one state in/out "
+                    "per launch, the kernel is instruction-issue bound (ncu: profiles/r01_summary.md), so the "
+                    "HBM fraction is low by construction")}
 
   # ---- CPU baseline beside it (rank 0, one core, bounded sample)
   cpu = None
