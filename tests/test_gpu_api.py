@@ -127,3 +127,15 @@ def test_vector_env_raise_on_invalid(cuda_device):
   venv = CircuitDesignerVectorEnv(4, 2, 12, 'SP-bell', raise_on_invalid=True); venv.reset()
   a = torch.tensor([[0, 0, 0, 0.1]] * 3 + [[0, 2, 0, 0.1]], device=cuda_device)
   with pytest.raises(AssertionError): venv.step(a)
+
+
+def test_smoke_without_programmatic_dependent_launch(cuda_device):
+  """QCD_PDL=0 (plain stream-ordered launches) must give the same results: run smoke() in a fresh
+  process with the switch off."""
+  import os, subprocess, sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, QCD_PDL="0")
+  res = subprocess.run([sys.executable, os.path.join(root, "__graft_entry__.py"), "smoke"], capture_output=True,
+                       text=True, timeout=300, cwd=root, env=env)
+  assert res.returncode == 0, res.stderr[-1500:]
+  assert res.stdout.count("match the oracle") == 2
