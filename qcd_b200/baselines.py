@@ -22,7 +22,7 @@ def sample_actions(n: int, qubits: int, generator: torch.Generator, device) -> t
   low = torch.as_tensor(sp.low, device=device, dtype=torch.float64)
   high = torch.as_tensor(sp.high, device=device, dtype=torch.float64)
   u = torch.rand((n, 4), generator=generator, device=device, dtype=torch.float64)
-  return (low + (high - low) * u).to(torch.float32).clamp_(sp.low.min().item(), None)
+  return (low + (high - low) * u).to(torch.float32)       # float32(high) < the next integer, so floor() stays in range
 
 
 def random_baseline(task: str, seeds: int = 8, episodes: int = 100, env_seed: int = 42, device=None) -> dict:
