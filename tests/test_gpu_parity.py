@@ -248,3 +248,27 @@ def test_maximum_depth_255_counter_boundary(cuda_device, objective, eta):
       np.testing.assert_allclose(gpu.reward.cpu().numpy(), ora.reward, atol=TOL, rtol=0)
   assert seen >= N
   _cmp(gpu, ora, what="end")
+
+
+@pytest.mark.parametrize("objective,eta,delta", [('SP-ghz5', 5, 20), ('UC-toffoli', 3, 30), ('SP-random', 10, 30)])
+def test_replay_with_per_env_targets(cuda_device, objective, eta, delta):
+  """Per-env targets take the general (first-generation) kernels in both step and replay mode."""
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(6)
+  N, T = 23, 30
+  S = 4 ** eta if 'UC' in objective else 2 ** eta
+  targets = rng.standard_normal((N, S)) + 1j * rng.standard_normal((N, S))
+  targets /= np.linalg.norm(targets, axis=1, keepdims=True)
+  a = EnvBatch(N, eta, delta, objective, targets)
+  b = EnvBatch(N, eta, delta, objective, targets)
+  ora = OracleBatch(N, eta, delta, objective, targets)
+  tape_np = uniform_box_tape(rng, eta, T, N)
+  tape = torch.as_tensor(tape_np, device=cuda_device)
+  b.replay(tape)
+  for t in range(T):
+    a.step(tape[t]); ora.step(tape_np[t])
+  assert torch.equal(a.state, b.state) and torch.equal(a.meta, b.meta)
+  assert torch.allclose(a.reward, b.reward, atol=1e-13, rtol=0)
+  np.testing.assert_allclose(b.state.cpu().numpy(), ora.state, atol=TOL, rtol=0)
+  np.testing.assert_allclose(b.reward.cpu().numpy(), ora.reward, atol=TOL, rtol=0)
+  np.testing.assert_array_equal(b.depth.cpu().numpy(), ora.depth)
