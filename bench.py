@@ -281,7 +281,8 @@ def run_native(args):
   from qcd_b200 import _lib as qlib
   shared_stats = torch.zeros((qlib.STATS_COPIES, qlib.STATS_STRIDE), dtype=torch.float64, device=dev)
   probe = EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
-                   fused_stats=not args.no_stats, device=dev, stats_buffer=shared_stats)
+                   fused_stats=not args.no_stats, device=dev, stats_buffer=shared_stats,
+                   actions_stable=args.actions_stable)
   S = probe.S
   bytes_step_env = probe.algorithmic_bytes_per_step()
   footprint = N * (16 * S + (8 * S if obs_mode != 'none' else 0) + 96)
@@ -290,7 +291,8 @@ def run_native(args):
   per_replica = N * (16 * S + (4 * probe.obs_stride if obs_mode != 'none' else 0) * (2 if args.final_obs else 1) + 200)
   R = max(1, min(R, int(0.8 * free // per_replica)))
   batches = [probe] + [EnvBatch(N, eta, delta, objective, target, obs_mode=obs_mode, final_obs=args.final_obs,
-                                fused_stats=not args.no_stats, device=dev, stats_buffer=shared_stats)
+                                fused_stats=not args.no_stats, device=dev, stats_buffer=shared_stats,
+                                actions_stable=args.actions_stable)
                        for _ in range(R - 1)]
   tape_np = make_tape(eta, TAPE_LEN if mode == 'step' else REPLAY_T * 2, N, seed=1234 + rank,
                       no_terminate=args.no_terminate)
@@ -541,6 +543,8 @@ def main():
   ap.add_argument("--obs", default="full", choices=["full", "state", "none"])
   ap.add_argument("--final-obs", action="store_true", help="also write terminal observations of finished envs")
   ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--actions-stable", action="store_true",
+                  help="QCD_F_ACTIONS_STABLE: the tape is pre-generated, decode before griddepcontrol.wait")
   ap.add_argument("--no-rotate", action="store_true", help="single batch replica (L2-resident at small sizes)")
   ap.add_argument("--no-terminate", action="store_true", help="action tape without Terminate (episodes end by depth)")
   ap.add_argument("--no-sweep", action="store_true", help="skip the secondary 1 Mi-env measurement")

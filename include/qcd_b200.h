@@ -8,7 +8,12 @@
  *   - every pointer inside qcd_batch_t is a DEVICE pointer (tensor.data_ptr()); the struct itself
  *     lives in host memory and is read during the call only (it may be reused / mutated afterwards);
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
- *   - calls are asynchronous on `stream`, never synchronise, never allocate, keep no global state;
+ *   - calls are asynchronous on `stream`, never synchronise (except qcd_step_sync), never allocate, and
+ *     keep no per-call state: the only process-wide state is idempotent and thread-safe (the QCD_PDL
+ *     environment switch read once; one "shared-memory opt-in done" bit per kernel and device);
+ *   - any of the per-step OUTPUT pointers, `obs` and the action pointer may also be pinned host memory
+ *     mapped into the device address space (cudaHostAlloc / UVA): the kernels then read the action and
+ *     write the results over PCIe directly (the single-env path does this, see qcd_step_sync);
  *   - return value: 0 ok, <0 invalid argument (QCD_E_*), >0 a cudaError_t from the launch;
  *     a batch with n_envs == 0 is a valid no-op;
  *   - the `_host` variants take HOST pointers for actions/results and issue the copies on `stream`.
@@ -26,7 +31,8 @@
  *              (env.py:10 `flat`); with obs_stride = 4*S the caller pre-fills the constant target
  *              half once and each row is exactly the reference observation (env.py:85)
  *   final_obs  same layout/stride as obs; written only for envs that finished this step when
- *              autoreset is on (the terminal observation); NULL = do not write
+ *              autoreset is on (the terminal observation); qcd_replay writes it at every reset of the
+ *              tape, so the buffer ends up as T qcd_step calls leave it; NULL = do not write
  */
 #ifndef QCD_B200_H
 #define QCD_B200_H
@@ -37,7 +43,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 4
+#define QCD_ABI_VERSION 5
 
 #define QCD_MAX_QUBITS_SP 12   /* S = 4096 complex128 = 64 KiB per env */
 #define QCD_MAX_QUBITS_UC 6    /* 64x64 unitary      = 64 KiB per env */
@@ -48,6 +54,13 @@ extern "C" {
 #define QCD_F_SPARSE          2u   /* env.py:134  zero reward/cost unless terminated|truncated */
 #define QCD_F_AUTORESET       4u   /* VectorEnv: reset finished envs inside the same launch    */
 #define QCD_F_TARGET_PER_ENV  8u   /* target is [N,S] instead of shared [S]                    */
+#define QCD_F_ACTIONS_STABLE 16u   /* the caller guarantees that the action buffer passed to qcd_step was
+                                      completely written BEFORE the previous kernel of the stream was
+                                      launched (pre-generated tapes).  qcd_step is launched with programmatic
+                                      stream serialization; with this flag it reads and decodes the action
+                                      before griddepcontrol.wait (overlapping the previous step's tail),
+                                      without it only after the wait, which is safe when the previous kernel
+                                      of the stream (a policy / sampler) produced the actions.            */
 
 /* objective */
 #define QCD_OBJ_SP 0               /* state preparation: fidelity |<psi|target>|^2  (env.py:109) */
@@ -151,6 +164,16 @@ int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int3
  * qcd_step / qcd_replay fuse when b->stats != NULL (do not use both on the same vector). */
 int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream);
 
+/* Folds the QCD_STATS_COPIES replicas into out[QCD_STATS_STRIDE] (device, float64; entries >= QCD_STATS_LEN
+ * are zero) with a one-warp kernel on `stream`, and clears the replicas when zero_raw != 0 (start of the
+ * next reporting interval).  `out` is what a rank hands to the statistics all-reduce (algorithm.py:99-114
+ * only logs these numbers, so the exchange can run on a side stream while the envs keep stepping). */
+int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream);
+
+/* qcd_step followed by cudaStreamSynchronize(stream) in one call: the single-env path (env.py:124-136 with
+ * numpy in / numpy out), where the action and every output live in mapped pinned host memory. */
+int qcd_step_sync(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream);
+
 /* HOST (pinned) destinations of qcd_step_host; every pointer may be NULL (field not copied back). */
 typedef struct qcd_host_out {
   double*  reward;          /* [N] */
@@ -168,7 +191,9 @@ typedef struct qcd_host_out {
 
 /* The reference's call with HOST buffers (env.step(action) -> obs, reward, terminated, truncated, info,
  * env.py:124-136): copy `actions_host` (pinned) to `actions_dev`, run qcd_step, copy the requested
- * results back into `out`'s host buffers; all on `stream`, no synchronisation (the caller syncs once). */
+ * results back into `out`'s host buffers; all on `stream`, no synchronisation (the caller syncs once, or
+ * keeps two env groups in flight on two streams).  When both the device rows (b->obs_stride) and the host
+ * rows (out->obs_stride) are compact (2*S floats) the observations move in one contiguous transfer. */
 int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_dev, int action_dtype,
                   const qcd_host_out_t* out, void* stream);
 

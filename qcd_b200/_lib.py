@@ -6,14 +6,14 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 STATS_LEN = 12
 STATS_COPIES = 64
 STATS_STRIDE = 16
 STAT_NAMES = ("episodes", "sum_r", "sum_l", "sum_d", "sum_o", "sum_q", "sum_m", "sum_c",
               "n_done", "n_depth", "steps", "bad_actions")
 
-F_PUNISH, F_SPARSE, F_AUTORESET, F_TARGET_PER_ENV = 1, 2, 4, 8
+F_PUNISH, F_SPARSE, F_AUTORESET, F_TARGET_PER_ENV, F_ACTIONS_STABLE = 1, 2, 4, 8, 16
 OBJ_SP, OBJ_UC = 0, 1
 ACT_F64, ACT_F32 = 0, 1
 ST_OK, ST_BAD_WIRE, ST_BAD_GATE = 0, 1, 2
@@ -53,7 +53,8 @@ class QcdHostOut(C.Structure):
               ("truncated", C.c_void_p), ("status", C.c_void_p), ("obs", C.c_void_p), ("obs_stride", C.c_int64)]
 
 
-EXPORTS = ("qcd_abi_version", "qcd_reset", "qcd_step", "qcd_replay", "qcd_reduce_stats", "qcd_step_host")
+EXPORTS = ("qcd_abi_version", "qcd_reset", "qcd_step", "qcd_replay", "qcd_reduce_stats", "qcd_fold_stats",
+           "qcd_step_sync", "qcd_step_host")
 
 _lib = None
 
@@ -64,14 +65,15 @@ def load_library(path: str | None = None) -> C.CDLL:
   if _lib is not None and path is None:
     return _lib
   p = path or LIB_PATH
-  if not os.path.exists(p) and path is None:
-    try:                                  # a fresh checkout: compile the real thing (needs nvcc) ...
-      from .build import build_library
-      build_library()
-    except Exception as exc:              # ... and fail loudly otherwise: there is nothing to fall back to
-      raise RuntimeError(
-          f"{p} is missing and could not be built ({exc}). Build it with `python -m qcd_b200.build` "
-          "(or __graft_entry__.build()). qcd_b200 has no CPU fallback.") from exc
+  if path is None:
+    from .build import build_library, is_stale
+    if is_stale():                        # missing, or built from other sources than the tree holds
+      try:                                # compile the real thing (needs nvcc) ...
+        build_library()
+      except Exception as exc:            # ... and fail loudly otherwise: there is nothing to fall back to
+        raise RuntimeError(
+            f"{p} is missing or stale and could not be rebuilt ({exc}). Build it with "
+            "`python -m qcd_b200.build` (or __graft_entry__.build()). qcd_b200 has no CPU fallback.") from exc
   if not os.path.exists(p):
     raise RuntimeError(f"{p} is missing. qcd_b200 has no CPU fallback.")
   lib = C.CDLL(p)
@@ -85,6 +87,10 @@ def load_library(path: str | None = None) -> C.CDLL:
   lib.qcd_replay.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_int, C.c_int32, C.POINTER(QcdTapeOut), C.c_void_p]
   lib.qcd_reduce_stats.restype = C.c_int
   lib.qcd_reduce_stats.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p]
+  lib.qcd_fold_stats.restype = C.c_int
+  lib.qcd_fold_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+  lib.qcd_step_sync.restype = C.c_int
+  lib.qcd_step_sync.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_int, C.c_void_p]
   lib.qcd_step_host.restype = C.c_int
   lib.qcd_step_host.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(QcdHostOut), C.c_void_p]
   if lib.qcd_abi_version() != ABI_VERSION:

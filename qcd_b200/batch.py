@@ -34,12 +34,16 @@ class EnvBatch:
   obs_mode: 'full'  -> obs rows are the reference observation [state | target] (4*S floats; the target
                        half is written once here and never touched by the kernels),
             'state' -> rows hold only the state half (2*S floats), 'none' -> no observations.
+  actions_stable: promise that every action tensor passed to `step` was completely written before the
+            previous kernel of the stream was launched (pre-generated tapes): QCD_F_ACTIONS_STABLE lets
+            the step kernel decode the action while the previous step drains.  Leave it off when a
+            policy / sampler kernel writes the actions right before `step`.
   """
 
   def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str, target,
                punish: bool = True, sparse: bool = True, autoreset: bool = True, obs_mode: str = 'full',
                final_obs: bool = False, track_episodes: bool = True, fused_stats: bool = True, device=None,
-               stats_buffer: torch.Tensor | None = None):
+               stats_buffer: torch.Tensor | None = None, actions_stable: bool = False):
     if not torch.cuda.is_available():
       raise RuntimeError("qcd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     self.lib = _lib.load_library()
@@ -107,7 +111,8 @@ class EnvBatch:
           self.final_obs[:, 2 * S:] = tflat
 
     flags = (_lib.F_PUNISH if self.punish else 0) | (_lib.F_SPARSE if self.sparse else 0) | \
-            (_lib.F_AUTORESET if self.autoreset else 0) | (_lib.F_TARGET_PER_ENV if self.per_env_target else 0)
+            (_lib.F_AUTORESET if self.autoreset else 0) | (_lib.F_TARGET_PER_ENV if self.per_env_target else 0) | \
+            (_lib.F_ACTIONS_STABLE if actions_stable else 0)
     d = self.max_depth
     self.c = QcdBatch(
         n_envs=N, n_qubits=self.qubits, objective=self.kind, max_depth=d, flags=flags, reserved0=0,
@@ -193,6 +198,17 @@ class EnvBatch:
 
   def zero_stats(self) -> None:
     self._stats_raw.zero_()
+
+  def fold_stats(self, out: torch.Tensor | None = None, zero: bool = False) -> torch.Tensor:
+    """Sum the atomic-spreading replicas into `out` (float64 [STATS_STRIDE], device) with ONE small kernel on
+    the current stream (capturable in a CUDA graph; no torch reduction), optionally clearing them: the
+    vector a rank hands to the statistics all-reduce at the end of a reporting interval."""
+    if out is None:
+      out = torch.empty(_lib.STATS_STRIDE, dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+      check(self.lib.qcd_fold_stats(self._stats_raw.data_ptr(), out.data_ptr(), int(zero), self._stream()),
+            "qcd_fold_stats")
+    return out
 
   # ------------------------------------------------------------------------------------------
   def state_view(self) -> torch.Tensor:

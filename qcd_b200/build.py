@@ -1,6 +1,7 @@
 """Build recipe for libqcd_b200.so (sm_100a only, in-tree so that the .so travels with the repo)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -8,6 +9,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "qcd_b200", "csrc")
 LIB_PATH = os.path.join(ROOT, "qcd_b200", "libqcd_b200.so")
+STAMP_PATH = LIB_PATH + ".srchash"        # content hash of the sources the library was built from
 SOURCES = [os.path.join(CSRC, "qcd_kernels.cu")]
 HEADERS = [os.path.join(ROOT, "include", "qcd_b200.h")]
 
@@ -26,24 +28,39 @@ def find_nvcc() -> str:
   return nvcc
 
 
+def source_hash() -> str:
+  """sha256 over the sources, the header, the flags and QCD_NVCC_EXTRA (mtimes do not survive a copy of
+  the tree to another box; contents do)."""
+  h = hashlib.sha256()
+  for p in SOURCES + HEADERS:
+    with open(p, "rb") as f:
+      h.update(f.read())
+  h.update(" ".join(NVCC_FLAGS[:-1]).encode())
+  h.update(os.environ.get("QCD_NVCC_EXTRA", "").encode())
+  return h.hexdigest()
+
+
 def is_stale() -> bool:
-  if not os.path.exists(LIB_PATH):
+  """True when libqcd_b200.so is missing or was built from other sources than the ones in the tree."""
+  if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
     return True
-  built = os.path.getmtime(LIB_PATH)
-  return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
+  with open(STAMP_PATH) as f:
+    return f.read().strip() != source_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
   """Compile csrc/*.cu -> qcd_b200/libqcd_b200.so.  Returns the library path."""
   if not force and not is_stale():
     return LIB_PATH
-  extra = os.environ.get("QCD_NVCC_EXTRA", "").split()      # tuning knobs, e.g. -DQCD_REG_MINB=3
+  extra = os.environ.get("QCD_NVCC_EXTRA", "").split()      # tuning knobs, e.g. -DQCD_WARP_CHUNK=4
   cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *SOURCES]
   if verbose:
     cmd.insert(1, "-Xptxas=-v")
   res = subprocess.run(cmd, capture_output=True, text=True)
   if res.returncode != 0:
     raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+  with open(STAMP_PATH, "w") as f:
+    f.write(source_hash() + "\n")
   if verbose:
     print(res.stderr)
   return LIB_PATH

@@ -37,6 +37,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "qcd_b200.h"
 
 namespace qcd {
@@ -585,7 +587,7 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
       const bool last = g.flags & RF_LAST;
       const bool wr_state = STAGED ? true : (g.kind != K_NONE || reset);
       float* ob = (b.obs && last) ? b.obs + genv * b.obs_stride : nullptr;
-      float* fob = (b.final_obs && last && reset && !STAGED) ? b.final_obs + genv * b.obs_stride : nullptr;
+      float* fob = (b.final_obs && reset) ? b.final_obs + genv * b.obs_stride : nullptr;   // every reset of a tape
       const unsigned lowmask = (1u << g.wbit) - 1u;
 #pragma unroll 1
       for (int j0 = 0; j0 < PPT; j0 += U) {
@@ -1082,14 +1084,20 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   EnvCtl e;
   e.meta = make_uint4(0, 0, 0, 0); e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
   // Programmatic dependent launch: this grid may have been started while the previous kernel of the
-  // stream (the previous env step) was still draining.  The action and its trig do not depend on
-  // that kernel; everything it wrote (meta, states, accumulators) is only touched after the wait.
+  // stream (the previous env step) was still draining.  Everything that kernel wrote (meta, states,
+  // accumulators) is only touched after the wait.
+  // The ACTION buffer is only read before the wait when the caller set QCD_F_ACTIONS_STABLE (it was
+  // complete before the previous kernel of the stream started, e.g. a pre-generated tape); otherwise
+  // a policy / sampling kernel may have written it right before this launch, and its writes are
+  // only guaranteed visible after griddepcontrol.wait.
   GateKind gk;
+  const bool early = b.flags & QCD_F_ACTIONS_STABLE;
+  if (!early) pdl_wait();
   if (ctl) {
     load_action(actions, act_f32, env, a0, a1, a2, a3);
     gk = decode_kind(b.n_qubits, a0, a1, a2, a3);
   }
-  pdl_wait();
+  if (early) pdl_wait();
   if (STAGE) {                                    // the tile goes in flight first
     if (lane == 0) {
       mbar_init(mbar, 1);
@@ -1400,6 +1408,10 @@ replay_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const 
     if (b.ep_return) { e.ep_ret = b.ep_return[env]; e.ep_len = b.ep_length[env]; }
   }
   double2* stp = stile + gi * S + li;
+  // terminal observations (QCD_F_AUTORESET + final_obs): written at EVERY reset of the tape, so that the
+  // buffer ends up exactly as T qcd_step launches leave it
+  float* fp = b.final_obs ? b.final_obs + (env_base + gi) * b.obs_stride + li : nullptr;
+  const long gstride = (long)G * b.obs_stride;
   double2 tv[V];
   double rv[V];
 #pragma unroll
@@ -1480,8 +1492,10 @@ replay_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const 
           }
           if (j == 0) metric_set<UC>(v, tv[j], ra, rb); else metric_acc<UC>(v, tv[j], ra, rb);
           if (act) {
-            if (reset) sp[L * j] = make_double2(rv[j], 0.0);
-            else if (kind != K_NONE) sp[L * j] = v;
+            if (reset) {
+              if (fp) { float* f = fp + (long)(c0 + k) * gstride; f[L * j] = (float)v.x; f[S + L * j] = (float)v.y; }
+              sp[L * j] = make_double2(rv[j], 0.0);
+            } else if (kind != K_NONE) sp[L * j] = v;
           }
         }
         part[k * ROW + lane] = make_double2(ra, rb);
@@ -1610,12 +1624,45 @@ stats_kernel(const qcd_batch_t b, double* __restrict__ stats) {
   }
 }
 
+// Sum of the QCD_STATS_COPIES replicas of the statistics vector in a fixed order -> out[QCD_STATS_STRIDE];
+// optionally clears the replicas (start of the next reporting interval).  One warp.
+__global__ void __launch_bounds__(32)
+fold_stats_kernel(double* __restrict__ raw, double* __restrict__ out, const int zero_raw) {
+  pdl_wait();
+  const int k = threadIdx.x;
+  if (k >= QCD_STATS_STRIDE) return;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < QCD_STATS_COPIES; ++c) {
+    acc += raw[c * QCD_STATS_STRIDE + k];
+    if (zero_raw) raw[c * QCD_STATS_STRIDE + k] = 0.0;
+  }
+  out[k] = k < QCD_STATS_LEN ? acc : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
+// The library keeps exactly two pieces of process-wide state, both idempotent and thread-safe: the
+// QCD_PDL environment switch (read once) and, per kernel instantiation, a bit per device saying that the
+// > 48 KiB dynamic shared memory opt-in has been made.
 static bool pdl_enabled() {     // QCD_PDL=0 in the environment turns programmatic dependent launch off
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("QCD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+  static const bool on = [] { const char* e = getenv("QCD_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+struct SmemOptIn { std::atomic<uint64_t> done[4]; };   // 256 devices
+template <typename Kern>
+static int ensure_smem(Kern kern, const size_t smem, SmemOptIn& once) {
+  if (smem <= 48 * 1024) return 0;
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return (int)err;
+  const uint64_t bit = 1ull << (dev & 63);
+  std::atomic<uint64_t>& word = once.done[(dev >> 6) & 3];
+  if (word.load(std::memory_order_acquire) & bit) return 0;
+  err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  word.fetch_or(bit, std::memory_order_release);
+  return 0;
 }
 constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
@@ -1639,14 +1686,8 @@ struct Launch {
       constexpr int MINB = S >= 4096 ? QCD_REPLAY_MINB : (S >= 2048 ? 4 : 6);   // smem allows 3 CTAs of 64 KiB
       auto kern = replay_cta_kernel<LOG2S, UC, RNT, MINB>;
       constexpr int BLOCK = RNT;
-      static bool attr_done[64] = {false};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (smem > 40 * 1024 && !attr_done[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        attr_done[dev & 63] = true;
-      }
+      static SmemOptIn once;
+      if (int rc = ensure_smem(kern, smem, once)) return rc;
       kern<<<(unsigned)b.n_envs, BLOCK, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
       return (int)cudaGetLastError();
     } else if constexpr (STAGED && S <= 256 && QCD_REPLAY_WARP) {
@@ -1658,14 +1699,8 @@ struct Launch {
       using WC = WarpCfg<LOG2S, TE, true>;
       constexpr size_t smem = (size_t)W * WC::WARP_SLOTS * sizeof(double2);
       auto kern = replay_warp_kernel<LOG2S, UC, W, TE, QCD_WARP_REPLAY_MINB>;
-      static bool attr_done[64] = {false};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (smem > 48 * 1024 && !attr_done[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        attr_done[dev & 63] = true;
-      }
+      static SmemOptIn once;
+      if (int rc = ensure_smem(kern, smem, once)) return rc;
       const long tiles = ((long)b.n_envs + TE - 1) / TE;
       const unsigned grid = (unsigned)((tiles + W - 1) / W);
       kern<<<grid, W * 32, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
@@ -1680,14 +1715,8 @@ struct Launch {
       using WC = WarpCfg<LOG2S, TE, STG>;
       constexpr size_t smem = (size_t)W * WC::WARP_SLOTS * sizeof(double2);
       auto kern = step_warp_kernel<LOG2S, UC, W, TE, STG, QCD_WARP_STEP_MINB>;
-      static bool attr_done[64] = {false};        // per device; set outside of any stream capture path
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (smem > 48 * 1024 && !attr_done[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        attr_done[dev & 63] = true;
-      }
+      static SmemOptIn once;
+      if (int rc = ensure_smem(kern, smem, once)) return rc;
       const long tiles = ((long)b.n_envs + TE - 1) / TE;
       const unsigned grid = (unsigned)((tiles + W - 1) / W);
       cudaLaunchConfig_t cfg = {};
@@ -1705,10 +1734,8 @@ struct Launch {
   static int run_pair(const qcd_batch_t& b, const void* actions, int act_f32, int T,
                       const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream) {
     auto kern = qcd_kernel<LOG2S, UC, STAGED, LOG2L, NT>;
-    if (SMEM > 48 * 1024) {
-      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-      if (err != cudaSuccess) return (int)err;
-    }
+    static SmemOptIn once;
+    if (int rc = ensure_smem(kern, SMEM, once)) return rc;
     const unsigned grid = (unsigned)((b.n_envs + E - 1) / E);
     kern<<<grid, NT, SMEM, stream>>>(b, actions, act_f32, T, out, metric_every_step);
     return (int)cudaGetLastError();
@@ -1807,6 +1834,18 @@ int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream) {
   return (int)cudaGetLastError();
 }
 
+int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream) {
+  if (!stats_raw || !out) return QCD_E_NULL;
+  qcd::fold_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_raw, out, zero_raw);
+  return (int)cudaGetLastError();
+}
+
+int qcd_step_sync(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream) {
+  int rc = qcd_step(b, actions, action_dtype, stream);
+  if (rc) return rc;
+  return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
 int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_dev, int action_dtype,
                   const qcd_host_out_t* out, void* stream) {
   if (b && b->n_envs == 0) return 0;          // empty batch: nothing to do
@@ -1816,10 +1855,26 @@ int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)b->n_envs;
   const size_t abytes = n * 4 * (action_dtype == QCD_ACT_F32 ? 4 : 8);
+  const int64_t S = b->objective == QCD_OBJ_UC ? (1LL << (2 * b->n_qubits)) : (1LL << b->n_qubits);
+  if (out->obs) {
+    if (!b->obs) return QCD_E_NULL;
+    if (out->obs_stride < 2 * S) return QCD_E_STRIDE;
+  }
   cudaError_t err = cudaMemcpyAsync(actions_dev, actions_host, abytes, cudaMemcpyHostToDevice, s);
   if (err != cudaSuccess) return (int)err;
   rc = qcd_step(b, actions_dev, action_dtype, stream);
   if (rc) return rc;
+  // the bulk of the bytes first: the state half of every observation row.  With compact rows on both
+  // sides (stride 2*S: obs_mode 'state') this is ONE contiguous transfer; otherwise a pitched one.
+  if (out->obs) {
+    if (out->obs_stride == 2 * S && b->obs_stride == 2 * S)
+      err = cudaMemcpyAsync(out->obs, b->obs, n * (size_t)(2 * S) * sizeof(float), cudaMemcpyDeviceToHost, s);
+    else
+      err = cudaMemcpy2DAsync(out->obs, (size_t)out->obs_stride * sizeof(float), b->obs,
+                              (size_t)b->obs_stride * sizeof(float), (size_t)(2 * S) * sizeof(float), n,
+                              cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return (int)err;
+  }
   const struct { void* dst; const void* src; size_t bytes; } copies[] = {
       {out->reward, b->reward, n * sizeof(double)},        {out->metric, b->metric, n * sizeof(double)},
       {out->cost, b->cost, n * sizeof(double)},            {out->depth, b->depth, n * sizeof(int32_t)},
@@ -1829,15 +1884,6 @@ int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_
   for (const auto& c : copies) {
     if (!c.dst) continue;
     err = cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, s);
-    if (err != cudaSuccess) return (int)err;
-  }
-  if (out->obs) {
-    if (!b->obs) return QCD_E_NULL;
-    const int64_t S = b->objective == QCD_OBJ_UC ? (1LL << (2 * b->n_qubits)) : (1LL << b->n_qubits);
-    if (out->obs_stride < 2 * S) return QCD_E_STRIDE;
-    err = cudaMemcpy2DAsync(out->obs, (size_t)out->obs_stride * sizeof(float), b->obs,
-                            (size_t)b->obs_stride * sizeof(float), (size_t)(2 * S) * sizeof(float), n,
-                            cudaMemcpyDeviceToHost, s);
     if (err != cudaSuccess) return (int)err;
   }
   return 0;

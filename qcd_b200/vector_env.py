@@ -116,7 +116,7 @@ class CircuitDesignerVectorEnv:
       if b.obs is not None:
         host['obs'] = torch.zeros((N, b.obs_stride), dtype=torch.float32, **pin)
         if b.obs_mode == 'full':
-          host['obs'][:, 2 * b.S:] = b.obs[0, 2 * b.S:].cpu()
+          host['obs'][:, 2 * b.S:] = b.obs[:, 2 * b.S:].cpu()      # per row: targets may differ per env
       ptr = lambda k: host[k].data_ptr()
       host['out_min'] = _lib.QcdHostOut(reward=ptr('reward'), terminated=ptr('terminated'), truncated=ptr('truncated'),
                                         obs_stride=b.obs_stride)

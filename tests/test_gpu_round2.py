@@ -1,0 +1,200 @@
+"""Round-2 parity tests: the holes VERDICT r01 named.
+
+* actions produced by a CUDA kernel launched right before every `qcd_step` (programmatic dependent
+  launch must not read them before `griddepcontrol.wait`), eager and inside a CUDA graph;
+* BASELINE.json configs[3] and configs[4] at their FULL sizes against the oracle on a strided sample;
+* the terminal observation of `qcd_replay`, per-env targets through `step_host`.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.batch_oracle import OracleBatch
+from oracle.qcd_oracle import make_target
+from tests.helpers import uniform_box_tape
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+OBS_TOL = 1.2e-7
+
+
+def _check(gpu, ora, sel=None, what=""):
+  """ints bit-exact, floats <= 1e-12, float32 observations <= 1 ulp; `sel` = env indices of `gpu` that `ora` holds."""
+  pick = (lambda t: t.cpu().numpy()) if sel is None else (lambda t: t[sel].cpu().numpy())
+  for name in ('depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status', 'meta', 'ep_length'):
+    np.testing.assert_array_equal(pick(getattr(gpu, name)), getattr(ora, name), err_msg=f"{what}:{name}")
+  for name in ('reward', 'metric', 'cost', 'ep_return', 'state'):
+    np.testing.assert_allclose(pick(getattr(gpu, name)), getattr(ora, name), atol=TOL, rtol=0, err_msg=f"{what}:{name}")
+  if gpu.obs is not None:
+    np.testing.assert_allclose(pick(gpu.obs), ora.obs, atol=OBS_TOL, rtol=0, err_msg=f"{what}:obs")
+
+
+@pytest.mark.parametrize("objective,eta,delta", [('SP-ghz5', 5, 20), ('UC-toffoli', 3, 30), ('SP-random', 9, 27)])
+@pytest.mark.parametrize("graphed", [False, True])
+def test_actions_written_by_a_kernel_right_before_every_step(cuda_device, objective, eta, delta, graphed):
+  """A policy stand-in (an elementwise torch kernel) overwrites ONE action buffer immediately before every
+  qcd_step on the same stream; with programmatic dependent launch on, a step that read its action before
+  `griddepcontrol.wait` would see the previous step's values and diverge from the oracle."""
+  from qcd_b200.batch import EnvBatch
+  S = 4 ** eta if 'UC' in objective else 2 ** eta
+  N, T = (65536, 200) if S <= 64 else (2048, 60)
+  rng = np.random.default_rng(17)
+  target = make_target(objective, eta, seed=2)
+  tape = uniform_box_tape(rng, eta, T, N)
+  tape[1::2, :, 0] = np.where(tape[1::2, :, 0] >= 2, 1.5, tape[1::2, :, 0])   # odd steps never Terminate: a stale
+  dtape = torch.as_tensor(tape, device=cuda_device)                          # action changes depth / state
+  gpu = EnvBatch(N, eta, delta, objective, target, device=cuda_device)
+  ora = OracleBatch(N, eta, delta, objective, target)
+  act = torch.zeros((N, 4), dtype=torch.float32, device=cuda_device)
+  one = torch.ones((), dtype=torch.float32, device=cuda_device)
+  checkpoints = sorted({0, 1, 2, T // 2, T - 1})
+  stream = torch.cuda.Stream(cuda_device)
+
+  def produce_and_step(t):
+    torch.mul(dtape[t], one, out=act)        # a kernel writes the action buffer ...
+    gpu.step(act)                            # ... and the env step follows on the same stream
+
+  done = 0
+  with torch.cuda.stream(stream):
+    if not graphed:
+      for t in range(T):
+        produce_and_step(t)
+        if t in checkpoints:
+          stream.synchronize()
+          while done <= t:
+            ora.step(tape[done]); done += 1
+          _check(gpu, ora, what=f"eager t={t}")
+    else:
+      produce_and_step(0)                    # lazy module loading outside of the capture
+      stream.synchronize()
+      gpu.reset(); gpu.zero_stats()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g, stream=stream):
+        for t in range(T):
+          produce_and_step(t)
+      gpu.reset(); gpu.zero_stats()
+      g.replay()
+      stream.synchronize()
+      for t in range(T): ora.step(tape[t])
+      _check(gpu, ora, what="graph")
+  assert gpu.stats[10].item() == N * T
+
+
+def test_config4_full_scale_sp_random12_one_million_envs(cuda_device):
+  """BASELINE.json configs[3] at full size on ONE GPU: SP-random eta=12, 1 Mi envs (64 GiB of states + 32 GiB of
+  state-half observations), punish=True; every 1024th env is checked against the oracle."""
+  from qcd_b200.batch import EnvBatch
+  free, _ = torch.cuda.mem_get_info(cuda_device)
+  if free < 112e9:
+    pytest.skip("needs ~100 GB of device memory")
+  N, eta, delta, T, stride = 1 << 20, 12, 36, 5, 1024
+  rng = np.random.default_rng(4)
+  target = make_target('SP-random', eta, seed=42)
+  gpu = EnvBatch(N, eta, delta, 'SP-random', target, obs_mode='state', punish=True, device=cuda_device)
+  sel = torch.arange(0, N, stride, device=cuda_device)
+  ora = OracleBatch(N // stride, eta, delta, 'SP-random', target, obs_mode='state', punish=True)
+  for t in range(T):
+    a = uniform_box_tape(rng, eta, 1, N)[0]
+    if t == T - 2: a[:, 0] = 2.5                    # everybody terminates once: metric + reset at full size
+    gpu.step(torch.as_tensor(a, device=cuda_device)); ora.step(a[::stride])
+    _check(gpu, ora, sel=sel, what=f"C4 t={t}")
+  st = gpu.stats.cpu().numpy()
+  assert st[10] == N * T and st[0] >= N
+  # size-independent property: every state is normalised (unitary evolution of e0)
+  nrm = torch.linalg.vector_norm(gpu.state, dim=1)
+  assert float((nrm - 1).abs().max()) < 1e-12
+  del gpu
+  torch.cuda.empty_cache()
+
+
+def test_config5_full_scale_uc_random6_replay(cuda_device):
+  """BASELINE.json configs[4] at full size: UC-random eta=6 (64x64 unitaries), 262 144 envs, one qcd_replay of
+  T=64 steps; every 256th env against the oracle stepping the same tape."""
+  from qcd_b200.batch import EnvBatch
+  free, _ = torch.cuda.mem_get_info(cuda_device)
+  if free < 40e9:
+    pytest.skip("needs ~30 GB of device memory")
+  N, eta, delta, T, stride = 262144, 6, 24, 64, 256
+  rng = np.random.default_rng(8)
+  target = make_target('UC-random', eta, seed=42)
+  gpu = EnvBatch(N, eta, delta, 'UC-random', target, obs_mode='state', device=cuda_device)
+  ora = OracleBatch(N // stride, eta, delta, 'UC-random', target, obs_mode='state')
+  tape = uniform_box_tape(rng, eta, T, N)
+  tape[:, 5 * stride] = uniform_box_tape(rng, eta, T, 1, no_terminate=True)[:, 0]   # one env runs into the depth limit
+  rec = {'reward': torch.zeros((T, N), dtype=torch.float64, device=cuda_device),
+         'depth': torch.zeros((T, N), dtype=torch.int32, device=cuda_device),
+         'terminated': torch.zeros((T, N), dtype=torch.uint8, device=cuda_device),
+         'truncated': torch.zeros((T, N), dtype=torch.uint8, device=cuda_device)}
+  gpu.replay(torch.as_tensor(tape, device=cuda_device), rec)
+  sel = torch.arange(0, N, stride, device=cuda_device)
+  for t in range(T):
+    ora.step(tape[t, ::stride])
+    np.testing.assert_allclose(rec['reward'][t, sel].cpu().numpy(), ora.reward, atol=TOL, rtol=0, err_msg=f"t={t}")
+    np.testing.assert_array_equal(rec['depth'][t, sel].cpu().numpy(), ora.depth, err_msg=f"t={t}")
+    np.testing.assert_array_equal(rec['terminated'][t, sel].cpu().numpy(), ora.terminated)
+    np.testing.assert_array_equal(rec['truncated'][t, sel].cpu().numpy(), ora.truncated)
+  assert rec['truncated'][:, 5 * stride].any()
+  _check(gpu, ora, sel=sel, what="C5 end")
+  assert gpu.stats[10].item() == N * T
+  # size-independent property: every resident V is unitary  (V^H V = I), checked on a random 4096-env subset
+  idx = torch.as_tensor(rng.choice(N, 4096, replace=False), device=cuda_device)
+  V = gpu.state_view()[idx]
+  eye = torch.eye(64, dtype=torch.complex128, device=cuda_device)
+  assert float((V.conj().transpose(1, 2) @ V - eye).abs().max()) < 1e-12
+  del gpu
+  torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("objective,eta,delta", [('SP-ghz5', 5, 20), ('UC-toffoli', 3, 30), ('SP-random', 10, 30), ('UC-random', 6, 24)])
+def test_replay_leaves_terminal_observations_like_steps(cuda_device, objective, eta, delta):
+  """final_obs after qcd_replay(T) == final_obs after T qcd_step calls (written at every reset of the tape)."""
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(31)
+  S = 4 ** eta if 'UC' in objective else 2 ** eta
+  N, T = (11, 24) if S >= 512 else (130, 40)
+  target = make_target(objective, eta, seed=3)
+  a = EnvBatch(N, eta, delta, objective, target, final_obs=True)
+  b = EnvBatch(N, eta, delta, objective, target, final_obs=True)
+  ora = OracleBatch(N, eta, delta, objective, target, final_obs=True)
+  tape_np = uniform_box_tape(rng, eta, T, N)
+  tape = torch.as_tensor(tape_np, device=cuda_device)
+  b.replay(tape)
+  seen = np.zeros(N, bool)
+  for t in range(T):
+    a.step(tape[t]); ora.step(tape_np[t])
+    seen |= (ora.terminated | ora.truncated).astype(bool)
+  assert seen.any()
+  assert torch.equal(a.final_obs, b.final_obs) and torch.equal(a.obs, b.obs)
+  np.testing.assert_allclose(b.final_obs.cpu().numpy()[seen], ora.final_obs[seen], atol=OBS_TOL, rtol=0)
+
+
+def test_step_host_with_per_env_targets_returns_each_envs_target_half(cuda_device):
+  from qcd_b200 import CircuitDesignerVectorEnv
+  rng = np.random.default_rng(5)
+  N, eta, delta = 64, 3, 9
+  targets = rng.standard_normal((N, 8)) + 1j * rng.standard_normal((N, 8))
+  targets /= np.linalg.norm(targets, axis=1, keepdims=True)
+  venv = CircuitDesignerVectorEnv(N, eta, delta, 'SP-random', target=targets)
+  ora = OracleBatch(N, eta, delta, 'SP-random', targets)
+  venv.reset()
+  for t in range(6):
+    a = uniform_box_tape(rng, eta, 1, N)[0]
+    obs, r, term, trunc = venv.step_host(a)
+    ora.step(a)
+    np.testing.assert_allclose(obs, ora.obs, atol=OBS_TOL, rtol=0)          # full rows: [state | own target]
+    np.testing.assert_allclose(r, ora.reward, atol=TOL, rtol=0)
+
+
+def test_fold_stats_sums_and_clears_the_replicas(cuda_device):
+  from qcd_b200 import _lib
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(2)
+  N, eta, delta = 4096, 3, 15
+  gpu = EnvBatch(N, eta, delta, 'SP-ghz3', make_target('SP-ghz3', eta))
+  tape = torch.as_tensor(uniform_box_tape(rng, eta, 12, N), device=cuda_device)
+  for t in range(12): gpu.step(tape[t])
+  want = gpu.stats.clone()
+  out = gpu.fold_stats(zero=True)
+  torch.cuda.synchronize()
+  assert torch.allclose(out[:_lib.STATS_LEN], want, rtol=1e-13, atol=0) and float(out[_lib.STATS_LEN:].abs().sum()) == 0
+  assert float(gpu._stats_raw.abs().sum()) == 0 and want[10].item() == 12 * N
