@@ -445,28 +445,59 @@ def run_native(args):
     e2e = {"value": None, "unit": UNIT, "skipped": "pinned host observation buffer would be "
            f"{host_obs_bytes / 1e9:.0f} GB" if host_obs_bytes > 8e9 else "--e2e-steps 0"}
   elif mode == 'step':
-    venv = CircuitDesignerVectorEnv(N, eta, delta, objective, target=target, device=dev, obs_mode=obs_mode)
+    # The reference-facing call with HOST buffers, every step: pinned host actions -> H2D -> step kernel ->
+    # D2H of reward / terminated / truncated and of the float32 state half of every observation row (the
+    # target half of env.py:85 is constant: `venv.target_obs`) -> host.  The envs are stepped as G groups
+    # on G streams (step_host_async / step_host_wait): a group's next actions are only submitted after its
+    # previous results have arrived on the host, so the RL data dependence holds per group while group g's
+    # D2H overlaps group g+1's H2D and kernel.  G = 1 is the plain synchronous step_host.
+    e2e_obs = 'none' if (obs_mode == 'none' or args.e2e_no_obs) else args.e2e_obs
+    venv = CircuitDesignerVectorEnv(N, eta, delta, objective, target=target, device=dev, obs_mode=e2e_obs)
     venv.reset()
     Ke = max(3, min(K, args.e2e_steps))
-    with torch.cuda.stream(stream):
-      for i in range(3):
-        venv.step_host(tape_np[i % TAPE_LEN], copy_obs=not args.e2e_no_obs)
-      if world > 1:
-        dist.barrier()
-      torch.cuda.synchronize(dev)
-      t0 = time.perf_counter()
-      for i in range(Ke):
-        venv.step_host(tape_np[i % TAPE_LEN], copy_obs=not args.e2e_no_obs)   # syncs every step
-      torch.cuda.synchronize(dev)
-      dt = time.perf_counter() - t0
+    G = max(1, args.e2e_groups)
+    ranges = venv.host_groups(G, np.float32)
+    consumed = 0.0
+
+    def e2e_loop(n_steps):
+      nonlocal consumed
+      if G == 1:
+        for i in range(n_steps):
+          out = venv.step_host(tape_np[i % TAPE_LEN], copy_obs=e2e_obs != 'none')
+          consumed += float(out[1][0])
+        return
+      for i in range(n_steps):
+        for g, (lo, hi) in enumerate(ranges):
+          if i > 0:
+            out = venv.step_host_wait(g)                 # results of step i-1 of this group are on the host
+            consumed += float(out[1][0])
+          venv.step_host_async(g, tape_np[i % TAPE_LEN, lo:hi], copy_obs=e2e_obs != 'none')
+      for g in range(G):
+        out = venv.step_host_wait(g)
+        consumed += float(out[1][0])
+
+    e2e_loop(3)
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e2e_loop(Ke)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
     t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
       dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    h2d, d2h = venv.host_bytes_per_step(np.float32, copy_obs=not args.e2e_no_obs)
+    h2d, d2h = venv.host_bytes_per_step(np.float32, copy_obs=e2e_obs != 'none')
     e2e = {"value": N * Ke * world / float(t_e.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "steps": Ke, "ms_per_step": float(t_e.item()) / Ke * 1e3,
-           "api": "CircuitDesignerVectorEnv.step_host -> qcd_step_host (pinned host buffers, sync per step)",
-           "obs_copied": not args.e2e_no_obs}
+           "d2h_gbs_per_gpu": d2h * Ke / float(t_e.item()) / 1e9,
+           "api": ("CircuitDesignerVectorEnv.step_host_async/step_host_wait -> qcd_step_host, %d env groups on %d "
+                   "streams (pinned host buffers, one event wait per group and step)" % (G, G)) if G > 1 else
+                  "CircuitDesignerVectorEnv.step_host -> qcd_step_host (pinned host buffers, sync per step)",
+           "groups": G, "obs_copied": e2e_obs != 'none',
+           "obs_rows": {"state": "compact state half [N, 2S] float32, one contiguous D2H", "full": "reference rows "
+                        "[N, 4S], pitched D2H of the state half", "none": "no observations"}[e2e_obs]}
+    del venv
 
   if rank != 0:
     if world > 1:
@@ -553,6 +584,9 @@ def main():
   ap.add_argument("--cpu-seconds", type=float, default=10.0)
   ap.add_argument("--e2e-steps", type=int, default=200)
   ap.add_argument("--e2e-no-obs", action="store_true", help="e2e without the observation D2H copy")
+  ap.add_argument("--e2e-groups", type=int, default=2, help="env groups in flight on the host path (1 = synchronous)")
+  ap.add_argument("--e2e-obs", default="state", choices=["state", "full"],
+                  help="host observation rows: compact state half (contiguous copy) or full reference rows (pitched)")
   ap.add_argument("--ref-envs-per-core", type=int, default=64)
   args = ap.parse_args()
   if args.warmup < 3:

@@ -34,6 +34,9 @@ class EnvBatch:
   obs_mode: 'full'  -> obs rows are the reference observation [state | target] (4*S floats; the target
                        half is written once here and never touched by the kernels),
             'state' -> rows hold only the state half (2*S floats), 'none' -> no observations.
+  host_outputs: the per-step outputs and the observation rows live in PINNED HOST memory, which UVA maps
+            into the device address space: the kernels write them over PCIe and the host reads them after a
+            stream synchronisation, with no copy call (the single-env path; sensible for a few envs only).
   actions_stable: promise that every action tensor passed to `step` was completely written before the
             previous kernel of the stream was launched (pre-generated tapes): QCD_F_ACTIONS_STABLE lets
             the step kernel decode the action while the previous step drains.  Leave it off when a
@@ -43,7 +46,8 @@ class EnvBatch:
   def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str, target,
                punish: bool = True, sparse: bool = True, autoreset: bool = True, obs_mode: str = 'full',
                final_obs: bool = False, track_episodes: bool = True, fused_stats: bool = True, device=None,
-               stats_buffer: torch.Tensor | None = None, actions_stable: bool = False):
+               stats_buffer: torch.Tensor | None = None, actions_stable: bool = False,
+               host_outputs: bool = False):
     if not torch.cuda.is_available():
       raise RuntimeError("qcd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     self.lib = _lib.load_library()
@@ -73,22 +77,24 @@ class EnvBatch:
     self.target = tgt.contiguous().to(dev)
 
     f64, i32, u8 = torch.float64, torch.int32, torch.uint8
+    self.host_outputs = bool(host_outputs)
+    odev = dict(device='cpu', pin_memory=True) if host_outputs else dict(device=dev)     # where outputs live
     self.state = torch.zeros((N, S), dtype=torch.complex128, device=dev)
     self.meta = torch.zeros((N, 16), dtype=u8, device=dev)
     self.last = torch.zeros((N, 2), dtype=f64, device=dev)
     self.ep_return = torch.zeros(N, dtype=f64, device=dev) if track_episodes else None
     self.ep_length = torch.zeros(N, dtype=i32, device=dev) if track_episodes else None
-    self.episode_return = torch.zeros(N, dtype=f64, device=dev) if track_episodes else None
-    self.episode_length = torch.zeros(N, dtype=i32, device=dev) if track_episodes else None
-    self.reward = torch.zeros(N, dtype=f64, device=dev)
-    self.metric = torch.zeros(N, dtype=f64, device=dev)
-    self.cost = torch.zeros(N, dtype=f64, device=dev)
-    self.depth = torch.zeros(N, dtype=i32, device=dev)
-    self.operations = torch.zeros(N, dtype=i32, device=dev)
-    self.used_wires = torch.zeros(N, dtype=i32, device=dev)
-    self.terminated = torch.zeros(N, dtype=u8, device=dev)
-    self.truncated = torch.zeros(N, dtype=u8, device=dev)
-    self.status = torch.zeros(N, dtype=torch.int8, device=dev)
+    self.episode_return = torch.zeros(N, dtype=f64, **odev) if track_episodes else None
+    self.episode_length = torch.zeros(N, dtype=i32, **odev) if track_episodes else None
+    self.reward = torch.zeros(N, dtype=f64, **odev)
+    self.metric = torch.zeros(N, dtype=f64, **odev)
+    self.cost = torch.zeros(N, dtype=f64, **odev)
+    self.depth = torch.zeros(N, dtype=i32, **odev)
+    self.operations = torch.zeros(N, dtype=i32, **odev)
+    self.used_wires = torch.zeros(N, dtype=i32, **odev)
+    self.terminated = torch.zeros(N, dtype=u8, **odev)
+    self.truncated = torch.zeros(N, dtype=u8, **odev)
+    self.status = torch.zeros(N, dtype=torch.int8, **odev)
     if stats_buffer is None:
       self._stats_raw = torch.zeros((_lib.STATS_COPIES, _lib.STATS_STRIDE), dtype=f64, device=dev)
     else:                       # several batches of one job may accumulate into a common vector
@@ -101,11 +107,12 @@ class EnvBatch:
     self.obs_stride = 2 * S
     if obs_mode != 'none':
       self.obs_stride = 4 * S if obs_mode == 'full' else 2 * S
-      self.obs = torch.zeros((N, self.obs_stride), dtype=torch.float32, device=dev)
+      self.obs = torch.zeros((N, self.obs_stride), dtype=torch.float32, **odev)
       if final_obs:
-        self.final_obs = torch.zeros((N, self.obs_stride), dtype=torch.float32, device=dev)
+        self.final_obs = torch.zeros((N, self.obs_stride), dtype=torch.float32, **odev)
       if obs_mode == 'full':                      # constant half: flat(target) (env.py:85)
         tflat = torch.cat([self.target.real, self.target.imag], dim=-1).to(torch.float32)
+        if host_outputs: tflat = tflat.cpu()
         self.obs[:, 2 * S:] = tflat
         if self.final_obs is not None:
           self.final_obs[:, 2 * S:] = tflat
@@ -163,6 +170,33 @@ class EnvBatch:
     actions, code = self._action_arg(actions, ())
     with torch.cuda.device(self.device):
       check(self.lib.qcd_step(self._cref, actions.data_ptr(), code, self._stream()), "qcd_step")
+
+  def step_sync(self, actions_ptr: int, code: int, stream_ptr: int) -> None:
+    """qcd_step + one stream synchronisation in ONE C call; `actions_ptr` may be mapped pinned host memory
+    (single-env path: action in, results out over PCIe without a copy call)."""
+    check(self.lib.qcd_step_sync(self._cref, actions_ptr, code, stream_ptr), "qcd_step_sync")
+
+  def sub_batch(self, lo: int, hi: int) -> QcdBatch:
+    """`qcd_batch_t` of the env range [lo, hi): the same buffers with every per-env pointer advanced by `lo`
+    rows (a group of envs that is stepped on its own stream; statistics go to the common vector)."""
+    if not 0 <= lo < hi <= self.num_envs:
+      raise ValueError((lo, hi))
+    c = QcdBatch()
+    C.pointer(c)[0] = self.c
+    c.n_envs = hi - lo
+    def adv(name, t, row_elems=None):
+      if t is None: return
+      row = t.stride(0) if row_elems is None else row_elems
+      setattr(c, name, t.data_ptr() + lo * row * t.element_size())
+    adv('state', self.state); adv('meta', self.meta); adv('last', self.last)
+    adv('ep_return', self.ep_return); adv('ep_length', self.ep_length)
+    adv('obs', self.obs); adv('final_obs', self.final_obs)
+    for name in ('reward', 'metric', 'cost', 'depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status',
+                 'episode_return', 'episode_length'):
+      adv(name, getattr(self, name))
+    if self.per_env_target:
+      adv('target', self.target)
+    return c
 
   def replay(self, tape: torch.Tensor, record: dict | None = None) -> None:
     """T fused steps with the states resident in shared memory.  tape: [T,N,4] on device.

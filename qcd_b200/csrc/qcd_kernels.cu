@@ -129,6 +129,9 @@ namespace qcd {
 #ifndef QCD_REPLAY_CTA
 #define QCD_REPLAY_CTA 1                // replay for S >= 512: CTA per env with decode-ahead (0: first version)
 #endif
+#ifndef QCD_REPLAY_IMPL
+#define QCD_REPLAY_IMPL 1               // replay for S >= 512: 1 register-resident (round 2), 0 shared-memory CTA kernel
+#endif
 #ifndef QCD_REPLAY_FUSE
 #define QCD_REPLAY_FUSE 1               // replay_cta_kernel: two consecutive gates per sweep over the state
 #endif
@@ -961,6 +964,345 @@ replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2b, round 2: replay for S >= 512 with each env's state resident in REGISTERS for the whole tape.
+//
+// ncu on replay_cta_kernel (profiles/r01_summary.md §4): 4 695 warp-instructions per env-step = 73 per
+// amplitude pair where an RX pair needs ~14; the index arithmetic, the per-pair switch, the shared-memory
+// round trip of every sweep and the bookkeeping replicated in 256 threads were the cost, not FP64.  Here
+//   * a CTA of S/16 threads owns one env; every thread keeps 16 amplitudes (4 "local" index bits) in
+//     registers.  The map position -> index bit is fixed at compile time (RegMap): positions 0..3 are the
+//     register bits, 4..8 the lane bits, 9.. the warp bits.  For UC the six (eta) ROW bits — the only bits
+//     a gate can act on — come first, so every UC gate is either pure register work (4 of 6 wires at
+//     eta=6) or one shuffle per amplitude (2 of 6); shared memory is not touched by a gate at all.  For SP
+//     the lane bits are index bits 0..4 (coalesced I/O), the register bits 5..8, and a gate on a warp bit
+//     (3 of 12 at eta=12) exchanges amplitudes through shared memory — diagonal gates never move data;
+//   * the gate of a step is dispatched ONCE per step to code specialised on (register bit, gate kind):
+//     no per-pair switch, no index arithmetic (the 16 register slots are compile-time);
+//   * the depth stack lives in the lanes (lane q = qubit q): two shuffles, one max and one REDUX.MAX per
+//     step and warp give every warp the depth / truncation / reset decision without a broadcast or barrier;
+//   * the action-only part of the decode (floor, kind, sincos) is done one step per thread ahead of time;
+//   * only steps that need the metric (episode end, last step; every step when dense or recorded) pay a
+//     block reduction + barrier; their finalize (atan, cost, records, statistics) rotates over the warps;
+//   * the target stays in L1/L2 (read only on metric steps), statistics are flushed once per launch.
+// Bit-identical amplitudes to qcd_step (same mul_phase / rot_rx).
+template <int LOG2S, bool UC>
+struct RegMap {
+  static constexpr int S = 1 << LOG2S;
+  static constexpr int NL = 4, A = 1 << NL;            // register bits, amplitudes per thread
+  static constexpr int NT = S >> NL;                   // threads per CTA (one env)
+  static constexpr int NW = NT / 32;                   // warps
+  static constexpr int ETA = UC ? LOG2S / 2 : LOG2S;
+  static_assert(NT >= 32, "replay_reg_kernel needs S >= 512");
+  __host__ __device__ static constexpr int bit_of_pos(const int p) {
+    return UC ? (p < ETA ? ETA + p : p - ETA)          // row bits first, then the column bits
+              : (p < 4 ? 5 + p : (p < 9 ? p - 4 : p)); // SP: registers 5..8, lanes 0..4, warps 9..
+  }
+  __host__ __device__ static constexpr int pos_of_bit(const int b) {
+    for (int p = 0; p < LOG2S; ++p) if (bit_of_pos(p) == b) return p;
+    return 0;
+  }
+  __host__ __device__ static constexpr unsigned long long pos_table() {   // 4 bits per index bit
+    unsigned long long t = 0;
+    for (int b = 0; b < LOG2S; ++b) t |= (unsigned long long)pos_of_bit(b) << (4 * b);
+    return t;
+  }
+  __host__ __device__ static constexpr int koff(const int k) {            // index offset of register slot k
+    int o = 0;
+    for (int j = 0; j < NL; ++j) if ((k >> j) & 1) o |= 1 << bit_of_pos(j);
+    return o;
+  }
+  // a gate can only target a warp position when one of the ACTIVE bits sits there
+  static constexpr bool WARP_TARGETS = UC ? (ETA > 9) : (LOG2S > 9);
+  static constexpr size_t XCHG_BYTES = WARP_TARGETS ? (size_t)S * sizeof(double2) : 0;
+};
+
+struct __align__(16) RegStep { double cr, sr; int pk; int pad; };
+// pk: [2:0] kind [4:3] status [5] term [9:6] w [13:10] c [17:14] target position [21:18] control position
+
+// slots k (of 16) whose bit j is set: 0xAAAA, 0xCCCC, 0xF0F0, 0xFF00
+__device__ __forceinline__ unsigned local_mask(const int j) { return (unsigned)(0xFF00F0F0CCCCAAAAull >> (16 * j)) & 0xffffu; }
+
+template <int J>
+__device__ __forceinline__ void reg_gate_local(const int kind, const unsigned cmask, const double cr, const double sr,
+                                               double2 (&a)[16]) {
+  constexpr int B = 1 << J;
+  switch (kind) {
+    case K_P:
+#pragma unroll
+      for (int k = 0; k < 16; ++k) if (k & B) a[k] = mul_phase(a[k], cr, sr);
+      break;
+    case K_CP:
+#pragma unroll
+      for (int k = 0; k < 16; ++k) if ((k & B) && ((cmask >> k) & 1u)) a[k] = mul_phase(a[k], cr, sr);
+      break;
+    case K_RX:
+#pragma unroll
+      for (int k = 0; k < 16; ++k) if (!(k & B)) {
+        const double2 n0 = rot_rx(a[k], a[k | B], cr, sr), n1 = rot_rx(a[k | B], a[k], cr, sr);
+        a[k] = n0; a[k | B] = n1;
+      }
+      break;
+    default:   // K_CX: swap the pair where the control bit is set (same for both members: c != w)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) if (!(k & B)) {
+        const bool sw = (cmask >> k) & 1u;
+        const double2 lo = a[k], hi = a[k | B];
+        a[k].x = sw ? hi.x : lo.x; a[k].y = sw ? hi.y : lo.y;
+        a[k | B].x = sw ? lo.x : hi.x; a[k | B].y = sw ? lo.y : hi.y;
+      }
+      break;
+  }
+}
+
+// target bit held by the thread index: `mine` = this thread's target bit, `p[k]` = the partner thread's slot k
+__device__ __forceinline__ void reg_gate_diag_thread(const int kind, const bool mine, const unsigned cmask,
+                                                     const double cr, const double sr, double2 (&a)[16]) {
+  if (!mine) return;
+  if (kind == K_P) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = mul_phase(a[k], cr, sr);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if ((cmask >> k) & 1u) a[k] = mul_phase(a[k], cr, sr);
+  }
+}
+
+template <int LOG2S, bool UC, int MINB>
+__global__ void __launch_bounds__(RegMap<LOG2S, UC>::NT, MINB)
+replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32, const int T,
+                  const qcd_tape_out_t out, const int metric_every_step) {
+  using M = RegMap<LOG2S, UC>;
+  constexpr int S = M::S, NT = M::NT, NW = M::NW, A = M::A;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned long long POS = M::pos_table();
+  extern __shared__ __align__(16) double2 s_xchg[];           // [S] exchange buffer (SP gates on warp bits)
+  __shared__ RegStep s_tab[NT];
+  __shared__ double2 s_wred[2][NW];
+  __shared__ double s_fin[4];                                 // ep_return, last_metric, last_cost
+  __shared__ double s_stats[QCD_STATS_LEN];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long env = blockIdx.x;
+  const long N = b.n_envs;
+  const bool autoreset = b.flags & QCD_F_AUTORESET;
+  const int shift = UC ? b.n_qubits : 0;
+  const unsigned tpat = (unsigned)tid << 4;                   // bit p (p >= 4) = this thread's bit at position p
+  int tbase = 0;
+#pragma unroll
+  for (int p = 4; p < LOG2S; ++p) tbase |= (int)((tpat >> p) & 1u) << M::bit_of_pos(p);
+  double2* gstate = reinterpret_cast<double2*>(b.state) + env * S + tbase;
+  const double2* tgt = reinterpret_cast<const double2*>(b.target) +
+                       ((b.flags & QCD_F_TARGET_PER_ENV) ? env * S : 0) + tbase;
+
+  double2 a[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) a[k] = gstate[M::koff(k)];
+  unsigned rmask = 0;                                         // slots that hold 1 after a reset (e0 / I)
+#pragma unroll
+  for (int k = 0; k < A; ++k) rmask |= (reset_amp(UC, b.n_qubits, tbase + M::koff(k)).x != 0.0 ? 1u : 0u) << k;
+
+  // bookkeeping, replicated per WARP: lane q holds the depth of qubit q (QuantumCircuit.depth stack)
+  const uint8_t* meta8 = reinterpret_cast<const uint8_t*>(b.meta) + env * 16;
+  int d = lane < 12 ? (int)meta8[lane] : 0;
+  const uint32_t mw = reinterpret_cast<const uint32_t*>(b.meta)[env * 4 + 3];
+  uint32_t ops = mw & 0xffffu, used = mw >> 16;
+  int ep_len = b.ep_return ? b.ep_length[env] : 0;
+  int n_bad = 0, n_metric = 0;
+  if (tid == 0) {
+    s_fin[0] = b.ep_return ? b.ep_return[env] : 0.0;
+    const double2 l2 = b.last ? reinterpret_cast<const double2*>(b.last)[env] : make_double2(0.0, 0.0);
+    s_fin[1] = l2.x; s_fin[2] = l2.y;
+  }
+  if (tid < QCD_STATS_LEN) s_stats[tid] = 0.0;
+  int par = 0;
+
+  for (int t0 = 0; t0 < T; t0 += NT) {
+    // ---- decode-ahead: step t0 + tid (env.py:90-100, the part that depends on the action alone)
+    if (t0 + tid < T) {
+      double a0, a1, a2, a3;
+      load_action(actions, act_f32, (long)(t0 + tid) * N + env, a0, a1, a2, a3);
+      const GateKind k = decode_kind(b.n_qubits, a0, a1, a2, a3);
+      RegStep r;
+      r.cr = k.cr; r.sr = k.sr; r.pad = 0;
+      const int tpos = (int)((POS >> (4 * (k.w + shift))) & 15ull), cpos = (int)((POS >> (4 * (k.c + shift))) & 15ull);
+      r.pk = k.kind | (k.status << 3) | ((k.term ? 1 : 0) << 5) | (k.w << 6) | (k.c << 10) | (tpos << 14) | (cpos << 18);
+      s_tab[tid] = r;
+    }
+    __syncthreads();
+    const int nsteps = (T - t0) < NT ? (T - t0) : NT;
+
+#pragma unroll 1
+    for (int si = 0; si < nsteps; ++si) {
+      const int t = t0 + si;
+      const double cr = s_tab[si].cr, sr = s_tab[si].sr;
+      const int pk = s_tab[si].pk;
+      const int kind = pk & 7, status = (pk >> 3) & 3;
+      const bool term = (pk >> 5) & 1;
+      // ---- the gate, on registers
+      if (kind != K_NONE) {
+        const int tpos = (pk >> 14) & 15, cpos = (pk >> 18) & 15;
+        unsigned cmask = 0xffffu;
+        if (kind == K_CP || kind == K_CX)
+          cmask = cpos < 4 ? local_mask(cpos) : (((tpat >> cpos) & 1u) ? 0xffffu : 0u);
+        if (tpos < 4) {
+          switch (tpos) {
+            case 0: reg_gate_local<0>(kind, cmask, cr, sr, a); break;
+            case 1: reg_gate_local<1>(kind, cmask, cr, sr, a); break;
+            case 2: reg_gate_local<2>(kind, cmask, cr, sr, a); break;
+            default: reg_gate_local<3>(kind, cmask, cr, sr, a); break;
+          }
+        } else if (kind == K_P || kind == K_CP) {              // diagonal: no data movement wherever the bit is
+          reg_gate_diag_thread(kind, (tpat >> tpos) & 1u, cmask, cr, sr, a);
+        } else if (tpos < 9) {                                 // partner = lane ^ xm: one shuffle per amplitude
+          const int xm = 1 << (tpos - 4);
+#pragma unroll
+          for (int k = 0; k < A; ++k) {
+            double2 p;
+            p.x = __shfl_xor_sync(FULL, a[k].x, xm);
+            p.y = __shfl_xor_sync(FULL, a[k].y, xm);
+            if (kind == K_RX) a[k] = rot_rx(a[k], p, cr, sr);
+            else if ((cmask >> k) & 1u) a[k] = p;              // CX
+          }
+        } else if (M::WARP_TARGETS) {                          // partner in another warp: through shared memory
+          const int ptid = tid ^ (1 << (tpos - 4));
+#pragma unroll
+          for (int k = 0; k < A; ++k) s_xchg[k * NT + tid] = a[k];
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < A; ++k) {
+            const double2 p = s_xchg[k * NT + ptid];
+            if (kind == K_RX) a[k] = rot_rx(a[k], p, cr, sr);
+            else if ((cmask >> k) & 1u) a[k] = p;
+          }
+          __syncthreads();                                     // buffer free for the next exchange
+        }
+      }
+
+      // ---- QuantumCircuit.depth / count_ops / idle_wires (env.py:74,77,86) + truncation (env.py:129)
+      if (kind != K_NONE) {
+        const int w = (pk >> 6) & 15, c = (pk >> 10) & 15;
+        const int dw = __shfl_sync(FULL, d, w), dc = __shfl_sync(FULL, d, c);
+        const int lvl = min(max(dw, dc) + 1, 255);             // saturate (only past truncation)
+        if (lane == w || lane == c) d = lvl;
+        ops = min(ops + 1u, 0xffffu);
+        used |= (1u << w) | (1u << c);
+      }
+      const int depth = __reduce_max_sync(FULL, d);
+      const bool ok = status == QCD_ST_OK;
+      const bool trunc = ok && (depth >= b.max_depth || (int)ops >= b.max_depth * b.n_qubits * 2);
+      const bool done = ok && (term || trunc);
+      const bool reset = done && autoreset;
+      const bool want_metric = metric_every_step || done || t == T - 1;
+      n_bad += !ok;
+
+      if (want_metric) {
+        // ---- env.py:106-111: |<psi|target>|^2  /  ||U - V||_F; block reduction riding on one barrier
+        double ra = 0.0, rb = 0.0;
+#pragma unroll
+        for (int k = 0; k < A; ++k) metric_acc<UC>(a[k], __ldg(tgt + M::koff(k)), ra, rb);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          ra += __shfl_xor_sync(FULL, ra, off);
+          if (!UC) rb += __shfl_xor_sync(FULL, rb, off);
+        }
+        if (lane == 0) s_wred[par][warp] = make_double2(ra, rb);
+        __syncthreads();
+        if (tid == (n_metric % NW) * 32) {                     // finalize rotates over the warps
+          double xa = 0.0, xb = 0.0;
+#pragma unroll
+          for (int wv = 0; wv < NW; ++wv) { xa += s_wred[par][wv].x; xb += s_wred[par][wv].y; }
+          EnvCtl e;
+          e.meta = make_uint4(0, 0, 0, 0);
+          e.ep_ret = s_fin[0]; e.last_m = s_fin[1]; e.last_c = s_fin[2]; e.ep_len = ep_len;
+          e.depth = depth; e.ops = (int)ops; e.used_cnt = __popc(used); e.status = status; e.term = term; e.trunc = trunc;
+          e.cost_raw = depth_cost(b, depth);
+          const StepOut o = finalize_step<UC>(b, e, xa, xb, true);
+          if (out.reward) out.reward[(long)t * N + env] = o.reward;
+          if (out.metric) out.metric[(long)t * N + env] = o.metric;
+          if (out.cost) out.cost[(long)t * N + env] = o.cost;
+          if (out.depth) out.depth[(long)t * N + env] = depth;
+          if (out.terminated) out.terminated[(long)t * N + env] = term;
+          if (out.truncated) out.truncated[(long)t * N + env] = trunc;
+          if (out.status) out.status[(long)t * N + env] = (int8_t)status;
+          if (t == T - 1) {
+            b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
+            b.depth[env] = depth; b.operations[env] = (int)ops; b.used_wires[env] = e.used_cnt;
+            b.terminated[env] = term; b.truncated[env] = trunc; b.status[env] = (int8_t)status;
+          }
+          if (done) {
+            if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
+            s_stats[QCD_STAT_EPISODES] += 1.0;
+            if (b.ep_return) { s_stats[QCD_STAT_SUM_R] += e.ep_ret; s_stats[QCD_STAT_SUM_L] += (double)e.ep_len; }
+            s_stats[QCD_STAT_SUM_D] += (double)depth; s_stats[QCD_STAT_SUM_O] += (double)ops;
+            s_stats[QCD_STAT_SUM_Q] += (double)e.used_cnt;
+            s_stats[QCD_STAT_SUM_M] += o.metric; s_stats[QCD_STAT_SUM_C] += o.cost;
+            s_stats[trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE] += 1.0;
+            if (autoreset) { e.ep_ret = 0.0; e.last_m = 0.0; e.last_c = 0.0; }
+          }
+          s_fin[0] = e.ep_ret; s_fin[1] = e.last_m; s_fin[2] = e.last_c;
+        }
+        par ^= 1; ++n_metric;
+      } else if (tid == 0) {
+        // ---- light step (sparse reward, episode goes on, nobody records the metric): reward and shaped cost
+        // are 0 (env.py:134), the metric is not evaluated (NaN in a record), ep_return is unchanged
+        if (out.reward) out.reward[(long)t * N + env] = 0.0;
+        if (out.cost) out.cost[(long)t * N + env] = ok ? 0.0 * 0.0 + depth_cost(b, depth) : depth_cost(b, depth);
+        if (out.depth) out.depth[(long)t * N + env] = depth;
+        if (out.terminated) out.terminated[(long)t * N + env] = term;
+        if (out.truncated) out.truncated[(long)t * N + env] = trunc;
+        if (out.status) out.status[(long)t * N + env] = (int8_t)status;
+      }
+      ep_len += ok;                                            // monitor.py:38 (every warp keeps its copy)
+
+      if (reset) {                                             // env.py:117-121 fused
+        if (b.final_obs) {                                     // terminal observation of this episode
+          float* fo = b.final_obs + env * b.obs_stride + tbase;
+#pragma unroll
+          for (int k = 0; k < A; ++k) { fo[M::koff(k)] = (float)a[k].x; fo[S + M::koff(k)] = (float)a[k].y; }
+        }
+#pragma unroll
+        for (int k = 0; k < A; ++k) a[k] = make_double2(((rmask >> k) & 1u) ? 1.0 : 0.0, 0.0);
+        // keeps this a real branch: if-converted into 64 selects per step, the compiler carried two copies of
+        // the state through the loop (128 MOVs + spills per step)
+        asm volatile("" ::: "memory");
+        d = 0; ops = 0; used = 0; ep_len = 0;
+      }
+    }
+    __syncthreads();                                           // the table may be overwritten by the next chunk
+  }
+
+  // ---- the state (and the observation of the last step) go back to HBM once
+  float* ob = b.obs ? b.obs + env * b.obs_stride + tbase : nullptr;
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    gstate[M::koff(k)] = a[k];
+    if (ob) { ob[M::koff(k)] = (float)a[k].x; ob[S + M::koff(k)] = (float)a[k].y; }
+  }
+  if (warp == 0) {
+    uint8_t* m8 = reinterpret_cast<uint8_t*>(b.meta) + env * 16;
+    if (lane < 12) m8[lane] = (uint8_t)d;
+    if (lane == 0) {
+      reinterpret_cast<uint32_t*>(b.meta)[env * 4 + 3] = ops | (used << 16);
+      if (b.ep_return) b.ep_length[env] = ep_len;
+    }
+  }
+  __syncthreads();                                             // the last finalizer's s_fin / s_stats
+  if (tid == 0) {
+    if (b.ep_return) b.ep_return[env] = s_fin[0];
+    if (b.last) reinterpret_cast<double2*>(b.last)[env] = make_double2(s_fin[1], s_fin[2]);
+  }
+  if (b.stats) {
+    double* stats = stats_slice(b, env);
+    if (tid < QCD_STATS_LEN) {
+      double v = s_stats[tid];
+      if (tid == QCD_STAT_STEPS) v = (double)(T - n_bad);
+      if (tid == QCD_STAT_BAD_ACTIONS) v = (double)n_bad;
+      if (v != 0.0) atomicAdd(stats + tid, v);
+    }
+  }
+}
+
 // ---- programmatic dependent launch (no-ops when the launch does not carry the attribute)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -1640,6 +1982,7 @@ fold_stats_kernel(double* __restrict__ raw, double* __restrict__ out, const int 
   out[k] = k < QCD_STATS_LEN ? acc : 0.0;
 }
 
+#ifndef QCD_KERNELS_ONLY   // (a scratch translation unit may include this file for the kernels alone)
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
 // The library keeps exactly two pieces of process-wide state, both idempotent and thread-safe: the
@@ -1680,7 +2023,15 @@ struct Launch {
 
   static int run(const qcd_batch_t& b, const void* actions, int act_f32, int T,
                  const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream) {
-    if constexpr (STAGED && S >= 512 && QCD_REPLAY_CTA) {
+    if constexpr (STAGED && S >= 512 && QCD_REPLAY_IMPL == 1) {
+      using M = RegMap<LOG2S, UC>;
+      constexpr int MINB = 512 / M::NT;                       // 16 warps per SM at <= 128 registers
+      auto kern = replay_reg_kernel<LOG2S, UC, MINB>;
+      static SmemOptIn once;
+      if (int rc = ensure_smem(kern, M::XCHG_BYTES, once)) return rc;
+      kern<<<(unsigned)b.n_envs, M::NT, M::XCHG_BYTES, stream>>>(b, actions, act_f32, T, out, metric_every_step);
+      return (int)cudaGetLastError();
+    } else if constexpr (STAGED && S >= 512 && QCD_REPLAY_CTA) {
       constexpr int RNT = (S / 2) < 256 ? (S / 2) : 256;
       constexpr size_t smem = (size_t)S * sizeof(double2);
       constexpr int MINB = S >= 4096 ? QCD_REPLAY_MINB : (S >= 2048 ? 4 : 6);   // smem allows 3 CTAs of 64 KiB
@@ -1890,3 +2241,4 @@ int qcd_step_host(const qcd_batch_t* b, const void* actions_host, void* actions_
 }
 
 }  // extern "C"
+#endif  // QCD_KERNELS_ONLY

@@ -2,16 +2,20 @@
 
 Drop-in for /root/reference/qcd_gym/env.py:13-141: same constructor kwargs, attributes, spaces,
 `reset` / `step` / `render` signatures, observation layout, info keys and exceptions.  The state
-lives on the GPU as a vector env of one env (autoreset off); every `step` is one `qcd_step_host`
-call (H2D action, step kernel, D2H of the observation and the scalars) and one synchronisation.
+lives on the GPU as a batch of one env (autoreset off).  The action buffer, the observation row and every
+per-step output live in pinned host memory that UVA maps into the device address space: the step kernel
+reads the action and writes its results over PCIe itself, so a `step` is ONE C call (`qcd_step_sync`:
+launch + stream synchronisation) with no copy calls on either side.
 """
 from __future__ import annotations
+
+import math
 
 import numpy as np
 
 from .gym_compat import Box, Env, np_random
 from .targets import make_target
-from .vector_env import GATES, CircuitDesignerVectorEnv, action_space_for
+from .vector_env import GATES, action_space_for
 
 
 class CircuitDesigner(Env):
@@ -32,11 +36,21 @@ class CircuitDesigner(Env):
     self.punish = punish; self.sparse = sparse
     self.objective = objective
     self.target = make_target(objective, max_qubits, seed)                        # env.py:40
-    self._venv = CircuitDesignerVectorEnv(1, max_qubits, max_depth, objective, punish=punish, sparse=sparse,
-                                          target=self.target, device=device, autoreset=False)
-    self._batch = self._venv.batch
+    import torch
+    from . import _lib
+    from .batch import EnvBatch
+    self._batch = b = EnvBatch(1, max_qubits, max_depth, objective, self.target, punish=punish, sparse=sparse,
+                               autoreset=False, device=device, host_outputs=True, fused_stats=False)
+    self._stream = torch.cuda.Stream(b.device)
+    self._sptr = self._stream.cuda_stream
+    self._act = torch.zeros((1, 4), dtype=torch.float64, pin_memory=True)       # mapped: read by the kernel
+    self._act_np, self._act_ptr, self._act_code = self._act.numpy()[0], self._act.data_ptr(), _lib.ACT_F64
+    self._torch = torch
+    # numpy views of the mapped outputs (valid after the synchronisation inside qcd_step_sync)
+    self._o = {k: getattr(b, k).numpy() for k in ('reward', 'metric', 'cost', 'depth', 'operations', 'used_wires',
+                                                  'terminated', 'truncated')}
+    self._obs_np = b.obs.numpy()[0]
     self._ops = []                         # host mirror of the circuit, used by render() only
-    b = self._batch
     self.observation_space = Box(low=-1.0, high=+1.0, shape=(4 * b.S,))           # env.py:44
     self.action_space = action_space_for(self.qubits)                             # env.py:46-49
 
@@ -44,8 +58,11 @@ class CircuitDesigner(Env):
   def _operation(self, action):
     """env.py:90-100: host-side replica of the decode, for the exceptions and for render()."""
     gate, wire, cntrl, theta = action
-    gate, wire, cntrl = np.floor([gate, wire, cntrl]).astype(int)
-    assert wire in range(self.qubits) and cntrl in range(self.qubits), f"{action}"
+    try:                                   # np.floor([...]).astype(int) of the reference, on Python floats
+      gate, wire, cntrl = math.floor(gate), math.floor(wire), math.floor(cntrl)
+    except (ValueError, OverflowError):    # nan / inf: the reference's int cast gives INT_MIN -> AssertionError
+      raise AssertionError(f"{action}") from None
+    assert 0 <= wire < self.qubits and 0 <= cntrl < self.qubits, f"{action}"
     if wire == cntrl and gate == 0: return ('p', [wire], float(theta))
     if wire == cntrl and gate == 1: return ('rx', [wire], float(theta))
     if gate == 0: return ('cp', [cntrl, wire], float(theta))
@@ -55,23 +72,26 @@ class CircuitDesigner(Env):
 
   def reset(self, seed=None, options=None):
     super().reset(seed=seed)
-    obs, _ = self._venv.reset()
+    with self._torch.cuda.stream(self._stream):
+      self._batch.reset()
+    self._stream.synchronize()
     self._ops = []
-    return obs[0].cpu().numpy(), {'depth': 0, 'operations': 0, 'used_wires': 0}
+    return self._obs_np.copy(), {'depth': 0, 'operations': 0, 'used_wires': 0}
 
   def step(self, action):
     operation = self._operation(action)              # raises AssertionError like env.py:94,100
     if operation is not None: self._ops.append(operation)
-    # one C-ABI call (H2D action, step kernel, D2H of the observation and every scalar) + one sync
-    obs, reward, term, trunc, inf = self._venv.step_host(np.asarray(action, dtype=np.float64).reshape(1, 4),
-                                                        copy_info=True)
-    terminated, truncated = bool(term[0]), bool(trunc[0])
-    info = {'depth': int(inf['depth'][0]), 'operations': int(inf['operations'][0]),
-            'used_wires': int(inf['used_wires'][0])}
+    # ONE C call: launch (the kernel reads the mapped action, writes the mapped results) + synchronise
+    self._act_np[:] = action
+    self._batch.step_sync(self._act_ptr, self._act_code, self._sptr)
+    o = self._o
+    terminated, truncated = bool(o['terminated'][0]), bool(o['truncated'][0])
+    info = {'depth': int(o['depth'][0]), 'operations': int(o['operations'][0]),
+            'used_wires': int(o['used_wires'][0])}
     if terminated: info['termination_reason'] = 'DONE'
     if truncated: info['termination_reason'] = 'DEPTH'                            # env.py:130-131
-    info = {**info, 'metric': float(inf['metric'][0]), 'cost': float(inf['cost'][0])}
-    return obs[0].copy(), float(reward[0]), terminated, truncated, info
+    info['metric'] = float(o['metric'][0]); info['cost'] = float(o['cost'][0])
+    return self._obs_np.copy(), float(o['reward'][0]), terminated, truncated, info
 
   # ------------------------------------------------------------------------------------------
   def render(self):

@@ -59,6 +59,7 @@ class CircuitDesignerVectorEnv:
     self.action_space = Box(np.tile(self.single_action_space.low, (self.num_envs, 1)),
                             np.tile(self.single_action_space.high, (self.num_envs, 1)))
     self._host = None
+    self._groups = None
 
   # ------------------------------------------------------------------------------------------
   def _info(self) -> dict:
@@ -114,17 +115,31 @@ class CircuitDesignerVectorEnv:
           'obs': None,
       }
       if b.obs is not None:
+        # same row width as on the device: 'full' rows carry the constant target half (pitched copy of the
+        # state half), 'state' rows are compact and move in ONE contiguous transfer
         host['obs'] = torch.zeros((N, b.obs_stride), dtype=torch.float32, **pin)
         if b.obs_mode == 'full':
           host['obs'][:, 2 * b.S:] = b.obs[:, 2 * b.S:].cpu()      # per row: targets may differ per env
-      ptr = lambda k: host[k].data_ptr()
-      host['out_min'] = _lib.QcdHostOut(reward=ptr('reward'), terminated=ptr('terminated'), truncated=ptr('truncated'),
-                                        obs_stride=b.obs_stride)
-      host['out_all'] = _lib.QcdHostOut(**{k: ptr(k) for k in ('reward', 'metric', 'cost', 'depth', 'operations',
-                                                               'used_wires', 'terminated', 'truncated', 'status')},
-                                        obs_stride=b.obs_stride)
+      host['np'] = {k: host[k].numpy() for k in ('actions', 'reward', 'metric', 'cost', 'depth', 'operations',
+                                                  'used_wires', 'terminated', 'truncated', 'status')}
+      host['np']['terminated'] = host['np']['terminated'].view(np.bool_)
+      host['np']['truncated'] = host['np']['truncated'].view(np.bool_)
+      host['np']['obs'] = None if host['obs'] is None else host['obs'].numpy()
       self._host = host
+      self._groups = None
     return self._host
+
+  def _host_out(self, h, lo, copy_obs, copy_info):
+    """qcd_host_out_t whose destinations are the rows [lo, ...) of the pinned host arrays."""
+    b = self.batch
+    names = ('reward', 'metric', 'cost', 'depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status') \
+        if copy_info else ('reward', 'terminated', 'truncated')
+    out = _lib.QcdHostOut(obs_stride=b.obs_stride)
+    for k in names:
+      setattr(out, k, h[k].data_ptr() + lo * h[k].element_size())
+    if copy_obs and h['obs'] is not None:
+      out.obs = h['obs'].data_ptr() + lo * b.obs_stride * 4
+    return out
 
   def step_host(self, actions, copy_obs: bool = True, copy_info: bool = False):
     """The end-to-end call with HOST buffers: numpy actions in, numpy results out.
@@ -133,26 +148,89 @@ class CircuitDesignerVectorEnv:
     (and the state half of every observation row; with copy_info also metric, cost, depth,
     operations, used_wires, status) are issued on the current stream by `qcd_step_host`, followed by
     one stream synchronisation.  Returned arrays are views of pinned host buffers that the next call
-    overwrites.  Returns (obs, reward, terminated, truncated[, info])."""
+    overwrites.  With obs_mode='state' the observation rows are the compact state halves [N, 2*S]
+    (one contiguous transfer; `target_obs` is the constant other half of env.py:85), with 'full' they are
+    the reference rows [N, 4*S].  Returns (obs, reward, terminated, truncated[, info])."""
     a = np.asarray(actions)
     dt = torch.float64 if a.dtype == np.float64 else torch.float32
     h = self._host_buffers(dt)
-    h['actions'].numpy()[...] = a.reshape(self.num_envs, 4)
+    h['np']['actions'][...] = a.reshape(self.num_envs, 4)
     b = self.batch
-    obs_h = h['obs'] if (copy_obs and h['obs'] is not None) else None
-    out = h['out_all'] if copy_info else h['out_min']
-    out.obs = None if obs_h is None else obs_h.data_ptr()
+    out = self._host_out(h, 0, copy_obs, copy_info)
     stream = torch.cuda.current_stream(self.device)
     with torch.cuda.device(self.device):
       _lib.check(b.lib.qcd_step_host(
           b._cref, h['actions'].data_ptr(), h['actions_dev'].data_ptr(),
           _lib.ACT_F64 if dt == torch.float64 else _lib.ACT_F32, out, stream.cuda_stream), "qcd_step_host")
     stream.synchronize()
-    res = (None if obs_h is None else obs_h.numpy(), h['reward'].numpy(),
-           h['terminated'].numpy().view(np.bool_), h['truncated'].numpy().view(np.bool_))
+    n = h['np']
+    res = (n['obs'] if (copy_obs and n['obs'] is not None) else None, n['reward'], n['terminated'], n['truncated'])
     if copy_info:
-      res += ({k: h[k].numpy() for k in ('metric', 'cost', 'depth', 'operations', 'used_wires', 'status')},)
+      res += ({k: n[k] for k in ('metric', 'cost', 'depth', 'operations', 'used_wires', 'status')},)
     return res
+
+  # ------------------------------------------------------------------------------------------
+  # Pipelined host path: the envs are split into `groups` contiguous groups, each stepped on its own stream.
+  # While group g's results travel to the host (D2H engine), group g+1's actions go up (H2D engine) and its
+  # kernel runs; the caller only ever supplies actions for a group AFTER it has received that group's previous
+  # results, so the RL data dependence (action_{t+1} depends on obs_t) is respected per group.
+  def host_groups(self, groups: int = 2, action_dtype=np.float32):
+    """[(lo, hi)] env ranges of the groups (creates streams / descriptors on first use)."""
+    dt = torch.float64 if np.dtype(action_dtype) == np.float64 else torch.float32
+    h = self._host_buffers(dt)
+    if self._groups is None or len(self._groups) != groups:
+      from .sharding import shard_range
+      self._groups = []
+      for g in range(groups):
+        lo, hi = shard_range(self.num_envs, g, groups)
+        self._groups.append({'lo': lo, 'hi': hi, 'c': self.batch.sub_batch(lo, hi),
+                             'stream': torch.cuda.Stream(self.device), 'event': torch.cuda.Event(),
+                             'pending': False, 'args': None})
+    return [(g['lo'], g['hi']) for g in self._groups]
+
+  def step_host_async(self, group: int, actions, copy_obs: bool = True, copy_info: bool = False) -> None:
+    """Submit one step of env group `group` (actions: [hi-lo, 4] host array) without waiting."""
+    import ctypes as C
+    a = np.asarray(actions)
+    dt = torch.float64 if a.dtype == np.float64 else torch.float32
+    h = self._host_buffers(dt)
+    if self._groups is None:
+      self.host_groups(2, a.dtype)
+    g = self._groups[group]
+    if g['pending']:
+      raise RuntimeError(f"group {group}: step_host_wait must collect the previous step first")
+    lo, hi = g['lo'], g['hi']
+    h['np']['actions'][lo:hi] = a.reshape(hi - lo, 4)
+    out = self._host_out(h, lo, copy_obs, copy_info)
+    esz = h['actions'].element_size() * 4
+    with torch.cuda.device(self.device):
+      _lib.check(self.batch.lib.qcd_step_host(
+          C.byref(g['c']), h['actions'].data_ptr() + lo * esz, h['actions_dev'].data_ptr() + lo * esz,
+          _lib.ACT_F64 if dt == torch.float64 else _lib.ACT_F32, out, g['stream'].cuda_stream), "qcd_step_host")
+    g['event'].record(g['stream'])
+    g['pending'], g['args'] = True, (copy_obs, copy_info)
+
+  def step_host_wait(self, group: int):
+    """Wait for the submitted step of `group`; returns views of rows [lo, hi) of the pinned host arrays:
+    (obs, reward, terminated, truncated[, info])."""
+    g = self._groups[group]
+    if not g['pending']:
+      raise RuntimeError(f"group {group}: nothing submitted")
+    g['event'].synchronize()
+    g['pending'] = False
+    copy_obs, copy_info = g['args']
+    n, lo, hi = self._host['np'], g['lo'], g['hi']
+    res = (n['obs'][lo:hi] if (copy_obs and n['obs'] is not None) else None, n['reward'][lo:hi],
+           n['terminated'][lo:hi], n['truncated'][lo:hi])
+    if copy_info:
+      res += ({k: n[k][lo:hi] for k in ('metric', 'cost', 'depth', 'operations', 'used_wires', 'status')},)
+    return res
+
+  @property
+  def target_obs(self) -> np.ndarray:
+    """float32 [2*S] (or [N, 2*S] with per-env targets): flat(target), the constant half of env.py:85."""
+    t = self.batch.target
+    return torch.cat([t.real, t.imag], dim=-1).to(torch.float32).cpu().numpy()
 
   def host_bytes_per_step(self, action_dtype=np.float32, copy_obs: bool = True):
     """(h2d, d2h) bytes `step_host` moves per call."""

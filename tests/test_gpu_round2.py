@@ -198,3 +198,56 @@ def test_fold_stats_sums_and_clears_the_replicas(cuda_device):
   torch.cuda.synchronize()
   assert torch.allclose(out[:_lib.STATS_LEN], want, rtol=1e-13, atol=0) and float(out[_lib.STATS_LEN:].abs().sum()) == 0
   assert float(gpu._stats_raw.abs().sum()) == 0 and want[10].item() == 12 * N
+
+
+@pytest.mark.parametrize("groups", [2, 3])
+def test_pipelined_host_groups_match_oracle(cuda_device, groups):
+  """step_host_async / step_host_wait: env groups stepped on their own streams; every group's results are
+  those of the oracle, whatever the interleaving, and the compact observation rows are the state halves."""
+  from qcd_b200 import CircuitDesignerVectorEnv
+  rng = np.random.default_rng(12)
+  N, eta, delta, T = 1000, 5, 20, 30
+  venv = CircuitDesignerVectorEnv(N, eta, delta, 'SP-ghz5', obs_mode='state')
+  ora = OracleBatch(N, eta, delta, 'SP-ghz5', venv.target, obs_mode='state')
+  venv.reset()
+  ranges = venv.host_groups(groups)
+  assert ranges[0][0] == 0 and ranges[-1][1] == N
+  tape = uniform_box_tape(rng, eta, T, N)
+  got = []
+  for t in range(T):
+    for g, (lo, hi) in enumerate(ranges):
+      if t > 0:
+        got.append((t - 1, lo, hi, [np.array(x) for x in venv.step_host_wait(g)[:4]]))
+      venv.step_host_async(g, tape[t, lo:hi])
+  with pytest.raises(RuntimeError): venv.step_host_async(0, tape[0, :ranges[0][1]])     # previous step not collected
+  for g, (lo, hi) in enumerate(ranges):
+    got.append((T - 1, lo, hi, [np.array(x) for x in venv.step_host_wait(g)[:4]]))
+  got.sort(key=lambda r: (r[0], r[1]))
+  it = iter(got)
+  for t in range(T):
+    ora.step(tape[t])
+    for _ in ranges:
+      tt, lo, hi, (obs, r, term, trunc) = next(it)
+      assert tt == t
+      np.testing.assert_allclose(obs, ora.obs[lo:hi], atol=OBS_TOL, rtol=0)
+      np.testing.assert_allclose(r, ora.reward[lo:hi], atol=TOL, rtol=0)
+      np.testing.assert_array_equal(term, ora.terminated[lo:hi].astype(bool))
+      np.testing.assert_array_equal(trunc, ora.truncated[lo:hi].astype(bool))
+  _check(venv.batch, ora, what="groups end")
+  tobs = venv.target_obs
+  assert tobs.shape == (64,) and tobs.dtype == np.float32
+  assert venv.episode_stats()['steps'] == N * T
+
+
+def test_single_env_zero_copy_outputs_are_fresh_arrays(cuda_device):
+  """The single-env path hands out copies (like the reference: fresh numpy arrays per step), not views of the
+  mapped buffers that the next step overwrites."""
+  import qcd_gym
+  from qcd_b200 import gym_compat as gym
+  qcd_gym.register_envs()
+  env = gym.make("CircuitDesigner-v0", max_qubits=2, max_depth=12, objective='SP-bell')
+  o0, _ = env.reset()
+  o1 = env.step([1, 0, 0, np.pi / 2])[0]
+  o2 = env.step([0, 0, 0, np.pi / 2])[0]
+  assert o0[0] == 1 and not np.array_equal(o1, o2) and not np.array_equal(o0, o1)
+  np.testing.assert_allclose(o1[:8], [np.sqrt(.5), 0, 0, 0, 0, -np.sqrt(.5), 0, 0], atol=1e-7)
