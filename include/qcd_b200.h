@@ -174,6 +174,12 @@ int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream);
  * numpy in / numpy out), where the action and every output live in mapped pinned host memory. */
 int qcd_step_sync(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream);
 
+/* env.step(action) of ONE env (b->n_envs == 1, env.py:124-136): `action` points to 4 doubles in ordinary host
+ * memory; they travel to the step kernel as a kernel argument (no H2D copy, no PCIe read), the kernel writes
+ * its results into b's (mapped pinned host) output buffers, and the call returns after
+ * cudaStreamSynchronize(stream). */
+int qcd_step1_sync(const qcd_batch_t* b, const double* action, void* stream);
+
 /* HOST (pinned) destinations of qcd_step_host; every pointer may be NULL (field not copied back). */
 typedef struct qcd_host_out {
   double*  reward;          /* [N] */

@@ -54,7 +54,7 @@ class QcdHostOut(C.Structure):
 
 
 EXPORTS = ("qcd_abi_version", "qcd_reset", "qcd_step", "qcd_replay", "qcd_reduce_stats", "qcd_fold_stats",
-           "qcd_step_sync", "qcd_step_host")
+           "qcd_step_sync", "qcd_step1_sync", "qcd_step_host")
 
 _lib = None
 
@@ -91,6 +91,8 @@ def load_library(path: str | None = None) -> C.CDLL:
   lib.qcd_fold_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
   lib.qcd_step_sync.restype = C.c_int
   lib.qcd_step_sync.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_int, C.c_void_p]
+  lib.qcd_step1_sync.restype = C.c_int
+  lib.qcd_step1_sync.argtypes = [C.POINTER(QcdBatch), C.POINTER(C.c_double), C.c_void_p]
   lib.qcd_step_host.restype = C.c_int
   lib.qcd_step_host.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(QcdHostOut), C.c_void_p]
   if lib.qcd_abi_version() != ABI_VERSION:

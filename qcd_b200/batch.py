@@ -84,17 +84,31 @@ class EnvBatch:
     self.last = torch.zeros((N, 2), dtype=f64, device=dev)
     self.ep_return = torch.zeros(N, dtype=f64, device=dev) if track_episodes else None
     self.ep_length = torch.zeros(N, dtype=i32, device=dev) if track_episodes else None
-    self.episode_return = torch.zeros(N, dtype=f64, **odev) if track_episodes else None
-    self.episode_length = torch.zeros(N, dtype=i32, **odev) if track_episodes else None
-    self.reward = torch.zeros(N, dtype=f64, **odev)
-    self.metric = torch.zeros(N, dtype=f64, **odev)
-    self.cost = torch.zeros(N, dtype=f64, **odev)
-    self.depth = torch.zeros(N, dtype=i32, **odev)
-    self.operations = torch.zeros(N, dtype=i32, **odev)
-    self.used_wires = torch.zeros(N, dtype=i32, **odev)
-    self.terminated = torch.zeros(N, dtype=u8, **odev)
-    self.truncated = torch.zeros(N, dtype=u8, **odev)
-    self.status = torch.zeros(N, dtype=torch.int8, **odev)
+    if host_outputs:
+      # ONE pinned allocation, carved into the output arrays grouped by dtype: the host reads
+      # [reward|metric|cost], [depth|operations|used_wires|episode_length], [terminated|truncated|status]
+      # as three contiguous blocks (`host_blocks`)
+      blob = torch.zeros(N * (4 * 8 + 4 * 4 + 3), dtype=u8, pin_memory=True)
+      f = blob[:N * 32].view(f64); i = blob[N * 32:N * 48].view(i32); u = blob[N * 48:]
+      self.reward, self.metric, self.cost, ep_r = f[:N], f[N:2 * N], f[2 * N:3 * N], f[3 * N:]
+      self.depth, self.operations, self.used_wires, ep_l = i[:N], i[N:2 * N], i[2 * N:3 * N], i[3 * N:]
+      self.terminated, self.truncated, self.status = u[:N], u[N:2 * N], u[2 * N:].view(torch.int8)
+      self.episode_return = ep_r if track_episodes else None
+      self.episode_length = ep_l if track_episodes else None
+      self.host_blocks = (f.numpy(), i.numpy(), u.numpy())
+      self._blob = blob
+    else:
+      self.episode_return = torch.zeros(N, dtype=f64, device=dev) if track_episodes else None
+      self.episode_length = torch.zeros(N, dtype=i32, device=dev) if track_episodes else None
+      self.reward = torch.zeros(N, dtype=f64, device=dev)
+      self.metric = torch.zeros(N, dtype=f64, device=dev)
+      self.cost = torch.zeros(N, dtype=f64, device=dev)
+      self.depth = torch.zeros(N, dtype=i32, device=dev)
+      self.operations = torch.zeros(N, dtype=i32, device=dev)
+      self.used_wires = torch.zeros(N, dtype=i32, device=dev)
+      self.terminated = torch.zeros(N, dtype=u8, device=dev)
+      self.truncated = torch.zeros(N, dtype=u8, device=dev)
+      self.status = torch.zeros(N, dtype=torch.int8, device=dev)
     if stats_buffer is None:
       self._stats_raw = torch.zeros((_lib.STATS_COPIES, _lib.STATS_STRIDE), dtype=f64, device=dev)
     else:                       # several batches of one job may accumulate into a common vector
@@ -173,8 +187,13 @@ class EnvBatch:
 
   def step_sync(self, actions_ptr: int, code: int, stream_ptr: int) -> None:
     """qcd_step + one stream synchronisation in ONE C call; `actions_ptr` may be mapped pinned host memory
-    (single-env path: action in, results out over PCIe without a copy call)."""
+    (action in, results out over PCIe without a copy call)."""
     check(self.lib.qcd_step_sync(self._cref, actions_ptr, code, stream_ptr), "qcd_step_sync")
+
+  def step1_sync(self, action4, stream_ptr: int) -> None:
+    """env.step of a batch of ONE env: `action4` is a ctypes array of 4 doubles that travels as a kernel
+    argument; returns after the stream synchronisation (outputs in mapped host memory are then valid)."""
+    check(self.lib.qcd_step1_sync(self._cref, action4, stream_ptr), "qcd_step1_sync")
 
   def sub_batch(self, lo: int, hi: int) -> QcdBatch:
     """`qcd_batch_t` of the env range [lo, hi): the same buffers with every per-env pointer advanced by `lo`

@@ -143,6 +143,7 @@ namespace qcd {
 #endif
 
 constexpr int K_NONE = 0, K_P = 1, K_RX = 2, K_CP = 3, K_CX = 4;
+constexpr int ACT_IMMEDIATE = 2;   // internal action mode of the step kernels: the (single) action is a kernel argument
 
 constexpr int RF_RESET = 1;    // episode finished and autoreset is on: state <- e0 / I after this step
 constexpr int RF_METRIC = 2;   // the metric of this step is needed
@@ -264,18 +265,19 @@ __device__ __forceinline__ void decode_action(const qcd_batch_t& b, double a0, d
 // env.py:106-114 + 133-135 + Monitor accumulators.  `ra`,`rb` are the reduced metric sums.
 struct StepOut { double reward, metric, cost; };
 
+// env.py:109 / env.py:111 from the reduced sums
 template <bool UC>
-__device__ __forceinline__ StepOut finalize_step(const qcd_batch_t& b, EnvCtl& e, double ra, double rb,
-                                                 bool have_metric) {
-  double metric_raw;
+__device__ __forceinline__ double metric_from_sums(const double ra, const double rb) {
   if (UC) {
     const double nrm = sqrt(ra);                               // ||U - V||_F
-    metric_raw = 1.0 - 2.0 * atan(nrm) / CUDART_PI;            // env.py:111
-  } else {
-    metric_raw = ra * ra + rb * rb;                            // env.py:109: abs(vdot)**2 (hypot-free:
-                                                               // within 2 ulp of numpy's hypot(re,im)**2)
+    return 1.0 - 2.0 * atan(nrm) / CUDART_PI;                  // env.py:111
   }
-  if (!have_metric) metric_raw = CUDART_NAN;
+  return ra * ra + rb * rb;                                    // env.py:109: abs(vdot)**2 (hypot-free:
+                                                               // within 2 ulp of numpy's hypot(re,im)**2)
+}
+
+// env.py:102-104 + 133-135 + Monitor accumulators, from the raw metric of the step
+__device__ __forceinline__ StepOut shape_step(const qcd_batch_t& b, EnvCtl& e, const double metric_raw) {
   StepOut o;
   if (e.status != QCD_ST_OK) {      // reference raises; batched path: env untouched, reward 0
     o.metric = metric_raw; o.cost = e.cost_raw; o.reward = 0.0;
@@ -295,6 +297,12 @@ __device__ __forceinline__ StepOut finalize_step(const qcd_batch_t& b, EnvCtl& e
   o.reward = r;
   e.ep_ret += r; e.ep_len += 1;                                // monitor.py:35,38
   return o;
+}
+
+template <bool UC>
+__device__ __forceinline__ StepOut finalize_step(const qcd_batch_t& b, EnvCtl& e, double ra, double rb,
+                                                 bool have_metric) {
+  return shape_step(b, e, have_metric ? metric_from_sums<UC>(ra, rb) : CUDART_NAN);
 }
 
 __device__ __forceinline__ double2 reset_amp(bool uc, int eta, int i) {
@@ -519,7 +527,7 @@ struct KCfg {
 template <int LOG2S, bool UC, bool STAGED, int LOG2L, int NT>
 __global__ void __launch_bounds__(NT)
 qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32, const int T,
-           const qcd_tape_out_t out, const int metric_every_step) {
+           const qcd_tape_out_t out, const int metric_every_step, const double4 imm) {
   using C = KCfg<LOG2S, UC, STAGED, LOG2L, NT>;
   constexpr int S = C::S, L = C::L, E = C::E, PPT = C::PPT, U = C::U;
 
@@ -571,7 +579,8 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
     // ================= phase 1: per-env scalar decode
     if (ctl) {
       double a0, a1, a2, a3;
-      load_action(actions, act_f32, (long)t * N + cenv, a0, a1, a2, a3);
+      if (act_f32 == ACT_IMMEDIATE) { a0 = imm.x; a1 = imm.y; a2 = imm.z; a3 = imm.w; }   // single env: action by value
+      else load_action(actions, act_f32, (long)t * N + cenv, a0, a1, a2, a3);
       GateRec rec;
       decode_action(b, a0, a1, a2, a3, e, rec);
       const bool done = e.term || e.trunc;
@@ -992,6 +1001,7 @@ struct RegMap {
   static constexpr int NL = 4, A = 1 << NL;            // register bits, amplitudes per thread
   static constexpr int NT = S >> NL;                   // threads per CTA (one env)
   static constexpr int NW = NT / 32;                   // warps
+  static constexpr int CH = 128;                       // steps decoded (and finalized) per chunk
   static constexpr int ETA = UC ? LOG2S / 2 : LOG2S;
   static_assert(NT >= 32, "replay_reg_kernel needs S >= 512");
   __host__ __device__ static constexpr int bit_of_pos(const int p) {
@@ -1055,38 +1065,26 @@ __device__ __forceinline__ void reg_gate_local(const int kind, const unsigned cm
   }
 }
 
-// target bit held by the thread index: `mine` = this thread's target bit, `p[k]` = the partner thread's slot k
-__device__ __forceinline__ void reg_gate_diag_thread(const int kind, const bool mine, const unsigned cmask,
-                                                     const double cr, const double sr, double2 (&a)[16]) {
-  if (!mine) return;
-  if (kind == K_P) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = mul_phase(a[k], cr, sr);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) if ((cmask >> k) & 1u) a[k] = mul_phase(a[k], cr, sr);
-  }
-}
-
 template <int LOG2S, bool UC, int MINB>
 __global__ void __launch_bounds__(RegMap<LOG2S, UC>::NT, MINB)
 replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32, const int T,
                   const qcd_tape_out_t out, const int metric_every_step) {
   using M = RegMap<LOG2S, UC>;
-  constexpr int S = M::S, NT = M::NT, NW = M::NW, A = M::A;
+  constexpr int S = M::S, NT = M::NT, NW = M::NW, A = M::A, CH = M::CH;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr unsigned long long POS = M::pos_table();
   extern __shared__ __align__(16) double2 s_xchg[];           // [S] exchange buffer (SP gates on warp bits)
-  __shared__ RegStep s_tab[NT];
-  __shared__ double2 s_wred[2][NW];
-  __shared__ double s_fin[4];                                 // ep_return, last_metric, last_cost
-  __shared__ double s_stats[QCD_STATS_LEN];
+  __shared__ RegStep s_tab[CH];                               // decoded steps of the chunk
+  __shared__ double2 s_msum[CH][NW];                          // per-warp metric sums of the chunk's metric steps
+  __shared__ int4 s_minfo[CH];                                // their bookkeeping: {t, depth|used<<8|flags<<16, ops, ep_len}
+  __shared__ double2 s_mres[CH];                              // their (raw metric, raw cost)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long env = blockIdx.x;
   const long N = b.n_envs;
   const bool autoreset = b.flags & QCD_F_AUTORESET;
   const int shift = UC ? b.n_qubits : 0;
+  const int max_ops = b.max_depth * b.n_qubits * 2;
   const unsigned tpat = (unsigned)tid << 4;                   // bit p (p >= 4) = this thread's bit at position p
   int tbase = 0;
 #pragma unroll
@@ -1103,45 +1101,66 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   for (int k = 0; k < A; ++k) rmask |= (reset_amp(UC, b.n_qubits, tbase + M::koff(k)).x != 0.0 ? 1u : 0u) << k;
 
   // bookkeeping, replicated per WARP: lane q holds the depth of qubit q (QuantumCircuit.depth stack)
-  const uint8_t* meta8 = reinterpret_cast<const uint8_t*>(b.meta) + env * 16;
-  int d = lane < 12 ? (int)meta8[lane] : 0;
+  int d = lane < 12 ? (int)reinterpret_cast<const uint8_t*>(b.meta)[env * 16 + lane] : 0;
   const uint32_t mw = reinterpret_cast<const uint32_t*>(b.meta)[env * 4 + 3];
   uint32_t ops = mw & 0xffffu, used = mw >> 16;
   int ep_len = b.ep_return ? b.ep_length[env] : 0;
-  int n_bad = 0, n_metric = 0;
+  // sequential episode state + statistics: shared memory, touched by thread 0 only (phase 2b)
+  __shared__ double s_seq[4 + QCD_STATS_LEN];                 // ep_return, last_metric, last_cost, -, statistics
+  __shared__ int s_nbad;                                      // steps with an invalid action (counted by the decode)
   if (tid == 0) {
-    s_fin[0] = b.ep_return ? b.ep_return[env] : 0.0;
+    s_nbad = 0;
+    s_seq[0] = b.ep_return ? b.ep_return[env] : 0.0;
     const double2 l2 = b.last ? reinterpret_cast<const double2*>(b.last)[env] : make_double2(0.0, 0.0);
-    s_fin[1] = l2.x; s_fin[2] = l2.y;
+    s_seq[1] = l2.x; s_seq[2] = l2.y;
+#pragma unroll
+    for (int k = 0; k < QCD_STATS_LEN; ++k) s_seq[4 + k] = 0.0;
   }
-  if (tid < QCD_STATS_LEN) s_stats[tid] = 0.0;
-  int par = 0;
 
-  for (int t0 = 0; t0 < T; t0 += NT) {
+  for (int t0 = 0; t0 < T; t0 += CH) {
     // ---- decode-ahead: step t0 + tid (env.py:90-100, the part that depends on the action alone)
-    if (t0 + tid < T) {
+    const int nsteps = (T - t0) < CH ? (T - t0) : CH;
+    for (int i = tid; i < nsteps; i += NT) {
       double a0, a1, a2, a3;
-      load_action(actions, act_f32, (long)(t0 + tid) * N + env, a0, a1, a2, a3);
+      load_action(actions, act_f32, (long)(t0 + i) * N + env, a0, a1, a2, a3);
       const GateKind k = decode_kind(b.n_qubits, a0, a1, a2, a3);
       RegStep r;
       r.cr = k.cr; r.sr = k.sr; r.pad = 0;
-      const int tpos = (int)((POS >> (4 * (k.w + shift))) & 15ull), cpos = (int)((POS >> (4 * (k.c + shift))) & 15ull);
-      r.pk = k.kind | (k.status << 3) | ((k.term ? 1 : 0) << 5) | (k.w << 6) | (k.c << 10) | (tpos << 14) | (cpos << 18);
-      s_tab[tid] = r;
+      int tpos = (int)((POS >> (4 * (k.w + shift))) & 15ull), cpos = (int)((POS >> (4 * (k.c + shift))) & 15ull);
+      // CP is symmetric in its two qubits: let the REGISTER-resident one play the target
+      if (k.kind == K_CP && tpos >= 4 && cpos < 4) { const int x = tpos; tpos = cpos; cpos = x; }
+      // bit 22: the metric of this step is needed whatever happens (recorded / dense reward / last step)
+      r.pk = k.kind | (k.status << 3) | ((k.term ? 1 : 0) << 5) | (k.w << 6) | (k.c << 10) | (tpos << 14) | (cpos << 18) |
+             ((metric_every_step || t0 + i == T - 1) ? (1 << 22) : 0);
+      s_tab[i] = r;
+      if (k.status != QCD_ST_OK) atomicAdd(&s_nbad, 1);
     }
-    __syncthreads();
-    const int nsteps = (T - t0) < NT ? (T - t0) : NT;
+    __syncthreads();                                          // table ready (and phase 2 of the previous chunk done)
+    int nm = 0;                                               // metric steps of this chunk so far
 
+    // ================= phase 1: the chunk's gates on registers; NO block-level synchronisation for UC
+    int n_pk = s_tab[0].pk;                                   // packed word of the next step, fetched one step ahead
 #pragma unroll 1
     for (int si = 0; si < nsteps; ++si) {
-      const int t = t0 + si;
       const double cr = s_tab[si].cr, sr = s_tab[si].sr;
-      const int pk = s_tab[si].pk;
-      const int kind = pk & 7, status = (pk >> 3) & 3;
-      const bool term = (pk >> 5) & 1;
-      // ---- the gate, on registers
+      const int pk = n_pk;
+      const int kind = pk & 7;
+      n_pk = s_tab[si + 1 < nsteps ? si + 1 : si].pk;
+      // ---- QuantumCircuit.depth / count_ops / idle_wires (env.py:74,77,86): issued BEFORE the gate (independent of
+      // it), so that the shuffle / REDUX latency hides behind the gate's arithmetic; consumed after it
+      if (kind != K_NONE) {
+        const int w = (pk >> 6) & 15, c = (pk >> 10) & 15;
+        const int dw = __shfl_sync(FULL, d, w), dc = __shfl_sync(FULL, d, c);
+        const int lvl = min(max(dw, dc) + 1, 255);             // saturate (only past truncation)
+        if (lane == w || lane == c) d = lvl;
+        ops = min(ops + 1u, 0xffffu);
+        used |= (1u << w) | (1u << c);
+      }
+      const int depth = __reduce_max_sync(FULL, d);
+
       if (kind != K_NONE) {
         const int tpos = (pk >> 14) & 15, cpos = (pk >> 18) & 15;
+        // slots (of 16) this gate touches as far as the CONTROL is concerned: all of them for P / RX
         unsigned cmask = 0xffffu;
         if (kind == K_CP || kind == K_CX)
           cmask = cpos < 4 ? local_mask(cpos) : (((tpat >> cpos) & 1u) ? 0xffffu : 0u);
@@ -1152,8 +1171,12 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
             case 2: reg_gate_local<2>(kind, cmask, cr, sr, a); break;
             default: reg_gate_local<3>(kind, cmask, cr, sr, a); break;
           }
-        } else if (kind == K_P || kind == K_CP) {              // diagonal: no data movement wherever the bit is
-          reg_gate_diag_thread(kind, (tpat >> tpos) & 1u, cmask, cr, sr, a);
+        } else if (kind == K_P || kind == K_CP) {
+          // diagonal, target (and for CP also the control) held by the thread index: all 16 slots or none
+          if (((tpat >> tpos) & 1u) && cmask) {
+#pragma unroll
+            for (int k = 0; k < A; ++k) a[k] = mul_phase(a[k], cr, sr);
+          }
         } else if (tpos < 9) {                                 // partner = lane ^ xm: one shuffle per amplitude
           const int xm = 1 << (tpos - 4);
 #pragma unroll
@@ -1179,83 +1202,47 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         }
       }
 
-      // ---- QuantumCircuit.depth / count_ops / idle_wires (env.py:74,77,86) + truncation (env.py:129)
-      if (kind != K_NONE) {
-        const int w = (pk >> 6) & 15, c = (pk >> 10) & 15;
-        const int dw = __shfl_sync(FULL, d, w), dc = __shfl_sync(FULL, d, c);
-        const int lvl = min(max(dw, dc) + 1, 255);             // saturate (only past truncation)
-        if (lane == w || lane == c) d = lvl;
-        ops = min(ops + 1u, 0xffffu);
-        used |= (1u << w) | (1u << c);
-      }
-      const int depth = __reduce_max_sync(FULL, d);
+      // ---- truncation (env.py:129), termination
+      const int status = (pk >> 3) & 3;
+      const bool term = (pk >> 5) & 1;
       const bool ok = status == QCD_ST_OK;
-      const bool trunc = ok && (depth >= b.max_depth || (int)ops >= b.max_depth * b.n_qubits * 2);
+      const bool trunc = ok && (depth >= b.max_depth || (int)ops >= max_ops);
       const bool done = ok && (term || trunc);
-      const bool reset = done && autoreset;
-      const bool want_metric = metric_every_step || done || t == T - 1;
-      n_bad += !ok;
+      const bool want_metric = done || ((pk >> 22) & 1);
 
       if (want_metric) {
-        // ---- env.py:106-111: |<psi|target>|^2  /  ||U - V||_F; block reduction riding on one barrier
-        double ra = 0.0, rb = 0.0;
+        // ---- env.py:106-111: partial sums of |<psi|target>|^2 / ||U - V||_F^2, one value per warp; they are
+        // combined, shaped and emitted in phase 2
+        double pa[4] = {0.0, 0.0, 0.0, 0.0}, pb[4] = {0.0, 0.0, 0.0, 0.0};   // four independent chains
 #pragma unroll
-        for (int k = 0; k < A; ++k) metric_acc<UC>(a[k], __ldg(tgt + M::koff(k)), ra, rb);
+        for (int k = 0; k < A; ++k) metric_acc<UC>(a[k], __ldg(tgt + M::koff(k)), pa[k & 3], pb[k & 3]);
+        double ra = (pa[0] + pa[1]) + (pa[2] + pa[3]), rb = (pb[0] + pb[1]) + (pb[2] + pb[3]);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
           ra += __shfl_xor_sync(FULL, ra, off);
           if (!UC) rb += __shfl_xor_sync(FULL, rb, off);
         }
-        if (lane == 0) s_wred[par][warp] = make_double2(ra, rb);
-        __syncthreads();
-        if (tid == (n_metric % NW) * 32) {                     // finalize rotates over the warps
-          double xa = 0.0, xb = 0.0;
-#pragma unroll
-          for (int wv = 0; wv < NW; ++wv) { xa += s_wred[par][wv].x; xb += s_wred[par][wv].y; }
-          EnvCtl e;
-          e.meta = make_uint4(0, 0, 0, 0);
-          e.ep_ret = s_fin[0]; e.last_m = s_fin[1]; e.last_c = s_fin[2]; e.ep_len = ep_len;
-          e.depth = depth; e.ops = (int)ops; e.used_cnt = __popc(used); e.status = status; e.term = term; e.trunc = trunc;
-          e.cost_raw = depth_cost(b, depth);
-          const StepOut o = finalize_step<UC>(b, e, xa, xb, true);
-          if (out.reward) out.reward[(long)t * N + env] = o.reward;
-          if (out.metric) out.metric[(long)t * N + env] = o.metric;
-          if (out.cost) out.cost[(long)t * N + env] = o.cost;
-          if (out.depth) out.depth[(long)t * N + env] = depth;
-          if (out.terminated) out.terminated[(long)t * N + env] = term;
-          if (out.truncated) out.truncated[(long)t * N + env] = trunc;
-          if (out.status) out.status[(long)t * N + env] = (int8_t)status;
-          if (t == T - 1) {
-            b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
-            b.depth[env] = depth; b.operations[env] = (int)ops; b.used_wires[env] = e.used_cnt;
-            b.terminated[env] = term; b.truncated[env] = trunc; b.status[env] = (int8_t)status;
-          }
-          if (done) {
-            if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
-            s_stats[QCD_STAT_EPISODES] += 1.0;
-            if (b.ep_return) { s_stats[QCD_STAT_SUM_R] += e.ep_ret; s_stats[QCD_STAT_SUM_L] += (double)e.ep_len; }
-            s_stats[QCD_STAT_SUM_D] += (double)depth; s_stats[QCD_STAT_SUM_O] += (double)ops;
-            s_stats[QCD_STAT_SUM_Q] += (double)e.used_cnt;
-            s_stats[QCD_STAT_SUM_M] += o.metric; s_stats[QCD_STAT_SUM_C] += o.cost;
-            s_stats[trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE] += 1.0;
-            if (autoreset) { e.ep_ret = 0.0; e.last_m = 0.0; e.last_c = 0.0; }
-          }
-          s_fin[0] = e.ep_ret; s_fin[1] = e.last_m; s_fin[2] = e.last_c;
-        }
-        par ^= 1; ++n_metric;
+        if (lane == 0) s_msum[nm][warp] = make_double2(ra, rb);
+        if (tid == 0)
+          s_minfo[nm] = make_int4(si, depth | (__popc(used) << 8) | (status << 16) | ((int)term << 18) | ((int)trunc << 19),
+                                  (int)ops, ep_len);
+        ++nm;
       } else if (tid == 0) {
         // ---- light step (sparse reward, episode goes on, nobody records the metric): reward and shaped cost
-        // are 0 (env.py:134), the metric is not evaluated (NaN in a record), ep_return is unchanged
-        if (out.reward) out.reward[(long)t * N + env] = 0.0;
-        if (out.cost) out.cost[(long)t * N + env] = ok ? 0.0 * 0.0 + depth_cost(b, depth) : depth_cost(b, depth);
-        if (out.depth) out.depth[(long)t * N + env] = depth;
-        if (out.terminated) out.terminated[(long)t * N + env] = term;
-        if (out.truncated) out.truncated[(long)t * N + env] = trunc;
-        if (out.status) out.status[(long)t * N + env] = (int8_t)status;
+        // are 0 (env.py:134), the metric is not evaluated, ep_return is unchanged
+        int tt = t0 + si;
+        asm volatile("" : "+r"(tt));                           // (no strength-reduced record pointers in the loop)
+        const long at = (long)tt * N + env;
+        if (out.reward) out.reward[at] = 0.0;
+        if (out.cost) out.cost[at] = depth_cost(b, depth);
+        if (out.depth) out.depth[at] = depth;
+        if (out.terminated) out.terminated[at] = term;
+        if (out.truncated) out.truncated[at] = trunc;
+        if (out.status) out.status[at] = (int8_t)status;
       }
       ep_len += ok;                                            // monitor.py:38 (every warp keeps its copy)
 
-      if (reset) {                                             // env.py:117-121 fused
+      if (done && autoreset) {                                 // env.py:117-121 fused
         if (b.final_obs) {                                     // terminal observation of this episode
           float* fo = b.final_obs + env * b.obs_stride + tbase;
 #pragma unroll
@@ -1269,7 +1256,55 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         d = 0; ops = 0; used = 0; ep_len = 0;
       }
     }
-    __syncthreads();                                           // the table may be overwritten by the next chunk
+    __syncthreads();                                           // every warp's sums of the chunk are in shared memory
+
+    // ================= phase 2a: raw metric (sqrt / atan) and raw cost of every metric step, one step per thread
+    for (int i = tid; i < nm; i += NT) {
+      double xa = 0.0, xb = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < NW; ++wv) { xa += s_msum[i][wv].x; xb += s_msum[i][wv].y; }
+      s_mres[i] = make_double2(metric_from_sums<UC>(xa, xb), depth_cost(b, s_minfo[i].y & 0xff));
+    }
+    __syncthreads();
+    // ================= phase 2b: the sequential part (env.py:102-104,133-135, Monitor, records), thread 0
+    if (tid == 0) {
+      EnvCtl e;
+      e.meta = make_uint4(0, 0, 0, 0);
+      e.ep_ret = s_seq[0]; e.last_m = s_seq[1]; e.last_c = s_seq[2];
+      double* st = s_seq + 4;
+      for (int i = 0; i < nm; ++i) {
+        const int4 mi = s_minfo[i];
+        const int t = t0 + mi.x, depth = mi.y & 0xff, used_cnt = (mi.y >> 8) & 0xff, status = (mi.y >> 16) & 3;
+        const bool term = (mi.y >> 18) & 1, trunc = (mi.y >> 19) & 1;
+        e.depth = depth; e.ops = mi.z; e.used_cnt = used_cnt; e.status = status; e.term = term; e.trunc = trunc;
+        e.ep_len = mi.w; e.cost_raw = s_mres[i].y;
+        const StepOut o = shape_step(b, e, s_mres[i].x);
+        const long at = (long)t * N + env;
+        if (out.reward) out.reward[at] = o.reward;
+        if (out.metric) out.metric[at] = o.metric;
+        if (out.cost) out.cost[at] = o.cost;
+        if (out.depth) out.depth[at] = depth;
+        if (out.terminated) out.terminated[at] = term;
+        if (out.truncated) out.truncated[at] = trunc;
+        if (out.status) out.status[at] = (int8_t)status;
+        if (t == T - 1) {
+          b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
+          b.depth[env] = depth; b.operations[env] = mi.z; b.used_wires[env] = used_cnt;
+          b.terminated[env] = term; b.truncated[env] = trunc; b.status[env] = (int8_t)status;
+        }
+        if (status == QCD_ST_OK && (term || trunc)) {
+          if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
+          st[QCD_STAT_EPISODES] += 1.0;
+          if (b.ep_return) { st[QCD_STAT_SUM_R] += e.ep_ret; st[QCD_STAT_SUM_L] += (double)e.ep_len; }
+          st[QCD_STAT_SUM_D] += (double)depth; st[QCD_STAT_SUM_O] += (double)mi.z; st[QCD_STAT_SUM_Q] += (double)used_cnt;
+          st[QCD_STAT_SUM_M] += o.metric; st[QCD_STAT_SUM_C] += o.cost;
+          if (trunc) st[QCD_STAT_N_DEPTH] += 1.0; else st[QCD_STAT_N_DONE] += 1.0;
+          if (autoreset) { e.ep_ret = 0.0; e.last_m = 0.0; e.last_c = 0.0; }
+        }
+      }
+      s_seq[0] = e.ep_ret; s_seq[1] = e.last_m; s_seq[2] = e.last_c;
+    }
+    // (the next chunk's first barrier orders these reads of s_minfo / s_mres before their next writes)
   }
 
   // ---- the state (and the observation of the last step) go back to HBM once
@@ -1280,25 +1315,17 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
     if (ob) { ob[M::koff(k)] = (float)a[k].x; ob[S + M::koff(k)] = (float)a[k].y; }
   }
   if (warp == 0) {
-    uint8_t* m8 = reinterpret_cast<uint8_t*>(b.meta) + env * 16;
-    if (lane < 12) m8[lane] = (uint8_t)d;
+    if (lane < 12) reinterpret_cast<uint8_t*>(b.meta)[env * 16 + lane] = (uint8_t)d;
     if (lane == 0) {
       reinterpret_cast<uint32_t*>(b.meta)[env * 4 + 3] = ops | (used << 16);
-      if (b.ep_return) b.ep_length[env] = ep_len;
-    }
-  }
-  __syncthreads();                                             // the last finalizer's s_fin / s_stats
-  if (tid == 0) {
-    if (b.ep_return) b.ep_return[env] = s_fin[0];
-    if (b.last) reinterpret_cast<double2*>(b.last)[env] = make_double2(s_fin[1], s_fin[2]);
-  }
-  if (b.stats) {
-    double* stats = stats_slice(b, env);
-    if (tid < QCD_STATS_LEN) {
-      double v = s_stats[tid];
-      if (tid == QCD_STAT_STEPS) v = (double)(T - n_bad);
-      if (tid == QCD_STAT_BAD_ACTIONS) v = (double)n_bad;
-      if (v != 0.0) atomicAdd(stats + tid, v);
+      if (b.ep_return) { b.ep_length[env] = ep_len; b.ep_return[env] = s_seq[0]; }
+      if (b.last) reinterpret_cast<double2*>(b.last)[env] = make_double2(s_seq[1], s_seq[2]);
+      if (b.stats) {
+        double* stats = stats_slice(b, env);
+        s_seq[4 + QCD_STAT_STEPS] = (double)(T - s_nbad); s_seq[4 + QCD_STAT_BAD_ACTIONS] = (double)s_nbad;
+#pragma unroll
+        for (int k = 0; k < QCD_STATS_LEN; ++k) if (s_seq[4 + k] != 0.0) atomicAdd(stats + k, s_seq[4 + k]);
+      }
     }
   }
 }
@@ -1394,7 +1421,7 @@ __device__ __forceinline__ int pack_gate(const GateRec& g) {
 //                  reduced with REDUX/shuffles and one atomicAdd per field per warp.
 template <int LOG2S, bool UC, int WARPS, int TE, bool STAGE, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32) {
+step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32, const double4 imm) {
   using W = WarpCfg<LOG2S, TE, STAGE>;
   constexpr int S = W::S, LOG2L = W::LOG2L, L = W::L, V = W::V, LOG2V = W::LOG2V, G = W::G, LOG2G = W::LOG2G;
   constexpr int R = W::R, C = W::C, PF = W::PF, ROW = W::ROW, SUMS = W::SUMS, P = W::P, VAL = W::VAL;
@@ -1436,7 +1463,8 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   const bool early = b.flags & QCD_F_ACTIONS_STABLE;
   if (!early) pdl_wait();
   if (ctl) {
-    load_action(actions, act_f32, env, a0, a1, a2, a3);
+    if (act_f32 == ACT_IMMEDIATE) { a0 = imm.x; a1 = imm.y; a2 = imm.z; a3 = imm.w; }     // single env: action by value
+    else load_action(actions, act_f32, env, a0, a1, a2, a3);
     gk = decode_kind(b.n_qubits, a0, a1, a2, a3);
   }
   if (early) pdl_wait();
@@ -1995,15 +2023,20 @@ static bool pdl_enabled() {     // QCD_PDL=0 in the environment turns programmat
 struct SmemOptIn { std::atomic<uint64_t> done[4]; };   // 256 devices
 template <typename Kern>
 static int ensure_smem(Kern kern, const size_t smem, SmemOptIn& once) {
-  if (smem <= 48 * 1024) return 0;
+  if (smem == 0) return 0;
   int dev = 0;
   cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return (int)err;
   const uint64_t bit = 1ull << (dev & 63);
   std::atomic<uint64_t>& word = once.done[(dev >> 6) & 3];
   if (word.load(std::memory_order_acquire) & bit) return 0;
-  err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncAttributes attr;                      // the 48 KiB default limit covers static + dynamic shared memory
+  err = cudaFuncGetAttributes(&attr, kern);
   if (err != cudaSuccess) return (int)err;
+  if (attr.sharedSizeBytes + smem > 48 * 1024) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+  }
   word.fetch_or(bit, std::memory_order_release);
   return 0;
 }
@@ -2022,7 +2055,7 @@ struct Launch {
   static constexpr bool REG = !STAGED && LOG2S <= QCD_REG_STEP_MAX_LOG2S;   // register-resident step
 
   static int run(const qcd_batch_t& b, const void* actions, int act_f32, int T,
-                 const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream) {
+                 const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream, const double4 imm) {
     if constexpr (STAGED && S >= 512 && QCD_REPLAY_IMPL == 1) {
       using M = RegMap<LOG2S, UC>;
       constexpr int MINB = 512 / M::NT;                       // 16 warps per SM at <= 128 registers
@@ -2042,7 +2075,7 @@ struct Launch {
       kern<<<(unsigned)b.n_envs, BLOCK, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
       return (int)cudaGetLastError();
     } else if constexpr (STAGED && S <= 256 && QCD_REPLAY_WARP) {
-      if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
+      if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream, imm);
       constexpr int W = QCD_WARP_REPLAY_WARPS;
       constexpr int G = S < 32 ? 32 / S : 1;
       constexpr int TE0 = clampi(QCD_WARP_REPLAY_TILE_BYTES / (S * 16), 1, 32);
@@ -2057,7 +2090,7 @@ struct Launch {
       kern<<<grid, W * 32, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
       return (int)cudaGetLastError();
     } else if constexpr (REG && QCD_STEP_IMPL == 2) {
-      if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
+      if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream, imm);
       constexpr int W = QCD_WARP_STEP_WARPS;
       constexpr int G = S < 32 ? 32 / S : 1;
       constexpr int TE0 = QCD_WARP_STEP_TILE > 0 ? QCD_WARP_STEP_TILE : clampi(8192 / (S * 16), 8, 32);
@@ -2076,35 +2109,35 @@ struct Launch {
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-      return (int)cudaLaunchKernelEx(&cfg, kern, b, actions, act_f32);
+      return (int)cudaLaunchKernelEx(&cfg, kern, b, actions, act_f32, imm);
     } else {
-      return run_pair(b, actions, act_f32, T, out, metric_every_step, stream);
+      return run_pair(b, actions, act_f32, T, out, metric_every_step, stream, imm);
     }
   }
 
   static int run_pair(const qcd_batch_t& b, const void* actions, int act_f32, int T,
-                      const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream) {
+                      const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream, const double4 imm) {
     auto kern = qcd_kernel<LOG2S, UC, STAGED, LOG2L, NT>;
     static SmemOptIn once;
     if (int rc = ensure_smem(kern, SMEM, once)) return rc;
     const unsigned grid = (unsigned)((b.n_envs + E - 1) / E);
-    kern<<<grid, NT, SMEM, stream>>>(b, actions, act_f32, T, out, metric_every_step);
+    kern<<<grid, NT, SMEM, stream>>>(b, actions, act_f32, T, out, metric_every_step, imm);
     return (int)cudaGetLastError();
   }
 };
 
 template <bool STAGED>
 int dispatch(const qcd_batch_t& b, const void* actions, int act_f32, int T, const qcd_tape_out_t& out,
-             int mes, cudaStream_t s) {
+             int mes, cudaStream_t s, const double4 imm = double4{0.0, 0.0, 0.0, 0.0}) {
   const bool uc = b.objective == QCD_OBJ_UC;
   const int log2s = uc ? 2 * b.n_qubits : b.n_qubits;
 #define QCD_CASE(LS)                                                                   \
   case LS:                                                                             \
-    return uc ? Launch<LS, true, STAGED>::run(b, actions, act_f32, T, out, mes, s)     \
-              : Launch<LS, false, STAGED>::run(b, actions, act_f32, T, out, mes, s);
+    return uc ? Launch<LS, true, STAGED>::run(b, actions, act_f32, T, out, mes, s, imm) \
+              : Launch<LS, false, STAGED>::run(b, actions, act_f32, T, out, mes, s, imm);
 #define QCD_CASE_SP(LS) \
   case LS:              \
-    return uc ? QCD_E_RANGE : Launch<LS, false, STAGED>::run(b, actions, act_f32, T, out, mes, s);
+    return uc ? QCD_E_RANGE : Launch<LS, false, STAGED>::run(b, actions, act_f32, T, out, mes, s, imm);
   switch (log2s) {
     QCD_CASE_SP(1) QCD_CASE(2) QCD_CASE_SP(3) QCD_CASE(4) QCD_CASE_SP(5) QCD_CASE(6)
     QCD_CASE_SP(7) QCD_CASE(8) QCD_CASE_SP(9) QCD_CASE(10) QCD_CASE_SP(11) QCD_CASE(12)
@@ -2193,6 +2226,18 @@ int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream) {
 
 int qcd_step_sync(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream) {
   int rc = qcd_step(b, actions, action_dtype, stream);
+  if (rc) return rc;
+  return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
+int qcd_step1_sync(const qcd_batch_t* b, const double* action, void* stream) {
+  int rc = qcd::validate(b, false, nullptr, QCD_ACT_F64);
+  if (rc) return rc;
+  if (!action) return QCD_E_NULL;
+  if (b->n_envs != 1) return QCD_E_RANGE;
+  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const double4 imm = {action[0], action[1], action[2], action[3]};      // travels as a kernel argument
+  rc = qcd::dispatch<false>(*b, nullptr, qcd::ACT_IMMEDIATE, 1, none, 1, (cudaStream_t)stream, imm);
   if (rc) return rc;
   return (int)cudaStreamSynchronize((cudaStream_t)stream);
 }

@@ -3,12 +3,13 @@
 Drop-in for /root/reference/qcd_gym/env.py:13-141: same constructor kwargs, attributes, spaces,
 `reset` / `step` / `render` signatures, observation layout, info keys and exceptions.  The state
 lives on the GPU as a batch of one env (autoreset off).  The action buffer, the observation row and every
-per-step output live in pinned host memory that UVA maps into the device address space: the step kernel
-reads the action and writes its results over PCIe itself, so a `step` is ONE C call (`qcd_step_sync`:
-launch + stream synchronisation) with no copy calls on either side.
+per-step output live in pinned host memory that UVA maps into the device address space: the action
+travels to the step kernel as a kernel argument and the kernel writes its results over PCIe itself, so a
+`step` is ONE C call (`qcd_step1_sync`: launch + stream synchronisation) with no copy on either side.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import numpy as np
@@ -43,12 +44,11 @@ class CircuitDesigner(Env):
                                autoreset=False, device=device, host_outputs=True, fused_stats=False)
     self._stream = torch.cuda.Stream(b.device)
     self._sptr = self._stream.cuda_stream
-    self._act = torch.zeros((1, 4), dtype=torch.float64, pin_memory=True)       # mapped: read by the kernel
-    self._act_np, self._act_ptr, self._act_code = self._act.numpy()[0], self._act.data_ptr(), _lib.ACT_F64
+    self._act = (ctypes.c_double * 4)()                 # the action travels as a kernel argument
     self._torch = torch
-    # numpy views of the mapped outputs (valid after the synchronisation inside qcd_step_sync)
-    self._o = {k: getattr(b, k).numpy() for k in ('reward', 'metric', 'cost', 'depth', 'operations', 'used_wires',
-                                                  'terminated', 'truncated')}
+    # the mapped outputs, grouped by dtype (valid after the synchronisation inside qcd_step1_sync):
+    # [reward, metric, cost, ep_r], [depth, operations, used_wires, ep_l], [terminated, truncated, status]
+    self._f, self._i, self._u = b.host_blocks
     self._obs_np = b.obs.numpy()[0]
     self._ops = []                         # host mirror of the circuit, used by render() only
     self.observation_space = Box(low=-1.0, high=+1.0, shape=(4 * b.S,))           # env.py:44
@@ -81,17 +81,18 @@ class CircuitDesigner(Env):
   def step(self, action):
     operation = self._operation(action)              # raises AssertionError like env.py:94,100
     if operation is not None: self._ops.append(operation)
-    # ONE C call: launch (the kernel reads the mapped action, writes the mapped results) + synchronise
-    self._act_np[:] = action
-    self._batch.step_sync(self._act_ptr, self._act_code, self._sptr)
-    o = self._o
-    terminated, truncated = bool(o['terminated'][0]), bool(o['truncated'][0])
-    info = {'depth': int(o['depth'][0]), 'operations': int(o['operations'][0]),
-            'used_wires': int(o['used_wires'][0])}
+    # ONE C call: launch (the action is a kernel argument, the kernel writes the mapped results) + synchronise
+    self._act[:] = action
+    self._batch.step1_sync(self._act, self._sptr)
+    reward, metric, cost, _ = self._f.tolist()
+    depth, operations, used_wires, _ = self._i.tolist()
+    terminated, truncated, _ = self._u.tolist()
+    terminated, truncated = terminated != 0, truncated != 0
+    info = {'depth': depth, 'operations': operations, 'used_wires': used_wires}
     if terminated: info['termination_reason'] = 'DONE'
     if truncated: info['termination_reason'] = 'DEPTH'                            # env.py:130-131
-    info['metric'] = float(o['metric'][0]); info['cost'] = float(o['cost'][0])
-    return self._obs_np.copy(), float(o['reward'][0]), terminated, truncated, info
+    info['metric'] = metric; info['cost'] = cost
+    return self._obs_np.copy(), reward, terminated, truncated, info
 
   # ------------------------------------------------------------------------------------------
   def render(self):
