@@ -1025,6 +1025,13 @@ struct RegMap {
   // a gate can only target a warp position when one of the ACTIVE bits sits there
   static constexpr bool WARP_TARGETS = UC ? (ETA > 9) : (LOG2S > 9);
   static constexpr size_t XCHG_BYTES = WARP_TARGETS ? (size_t)S * sizeof(double2) : 0;
+  // UC: a warp's 16-byte target loads of one slot touch four separate 128-byte lines (two lane bits are the high
+  // row bits), which costs the L1 data pipe 4x the cycles of a contiguous access; every thread therefore parks ITS
+  // 16 target amplitudes in shared memory once per launch ([slot][thread]: conflict-free, private, no barrier).
+  // SP lanes are index bits 0..4: the loads are contiguous and stay on the L1 path.
+  static constexpr bool TGT_SMEM = UC;
+  static constexpr size_t TGT_BYTES = TGT_SMEM ? (size_t)S * sizeof(double2) : 0;
+  static constexpr size_t DYN_BYTES = XCHG_BYTES + TGT_BYTES;
 };
 
 struct __align__(16) RegStep { double cr, sr; int pk; int pad; };
@@ -1073,7 +1080,9 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   constexpr int S = M::S, NT = M::NT, NW = M::NW, A = M::A, CH = M::CH;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr unsigned long long POS = M::pos_table();
-  extern __shared__ __align__(16) double2 s_xchg[];           // [S] exchange buffer (SP gates on warp bits)
+  extern __shared__ __align__(16) double2 s_dynamic[];
+  double2* const s_xchg = s_dynamic;                          // [S] exchange buffer (SP gates on warp bits)
+  double2* const s_tgt = s_dynamic + M::XCHG_BYTES / sizeof(double2) + threadIdx.x;   // [16][NT] this thread's target slots
   __shared__ RegStep s_tab[CH];                               // decoded steps of the chunk
   __shared__ double2 s_msum[CH][NW];                          // per-warp metric sums of the chunk's metric steps
   __shared__ int4 s_minfo[CH];                                // their bookkeeping: {t, depth|used<<8|flags<<16, ops, ep_len}
@@ -1096,6 +1105,10 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   double2 a[A];
 #pragma unroll
   for (int k = 0; k < A; ++k) a[k] = gstate[M::koff(k)];
+  if (M::TGT_SMEM) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) s_tgt[k * NT] = __ldg(tgt + M::koff(k));
+  }
   unsigned rmask = 0;                                         // slots that hold 1 after a reset (e0 / I)
 #pragma unroll
   for (int k = 0; k < A; ++k) rmask |= (reset_amp(UC, b.n_qubits, tbase + M::koff(k)).x != 0.0 ? 1u : 0u) << k;
@@ -1215,7 +1228,8 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         // combined, shaped and emitted in phase 2
         double pa[4] = {0.0, 0.0, 0.0, 0.0}, pb[4] = {0.0, 0.0, 0.0, 0.0};   // four independent chains
 #pragma unroll
-        for (int k = 0; k < A; ++k) metric_acc<UC>(a[k], __ldg(tgt + M::koff(k)), pa[k & 3], pb[k & 3]);
+        for (int k = 0; k < A; ++k)
+          metric_acc<UC>(a[k], M::TGT_SMEM ? s_tgt[k * NT] : __ldg(tgt + M::koff(k)), pa[k & 3], pb[k & 3]);
         double ra = (pa[0] + pa[1]) + (pa[2] + pa[3]), rb = (pb[0] + pb[1]) + (pb[2] + pb[3]);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -1307,12 +1321,18 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
     // (the next chunk's first barrier orders these reads of s_minfo / s_mres before their next writes)
   }
 
-  // ---- the state (and the observation of the last step) go back to HBM once
-  float* ob = b.obs ? b.obs + env * b.obs_stride + tbase : nullptr;
+  // ---- the state (and the observation of the last step) go back to HBM once.  The addresses are rebuilt from
+  // a fresh read of the CTA index, so that no pointer has to stay in a register through the step loop.
+  {
+    unsigned cta;
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
+    double2* gs = reinterpret_cast<double2*>(b.state) + (long)cta * S + tbase;
+    float* ob = b.obs ? b.obs + (long)cta * b.obs_stride + tbase : nullptr;
 #pragma unroll
-  for (int k = 0; k < A; ++k) {
-    gstate[M::koff(k)] = a[k];
-    if (ob) { ob[M::koff(k)] = (float)a[k].x; ob[S + M::koff(k)] = (float)a[k].y; }
+    for (int k = 0; k < A; ++k) {
+      gs[M::koff(k)] = a[k];
+      if (ob) { ob[M::koff(k)] = (float)a[k].x; ob[S + M::koff(k)] = (float)a[k].y; }
+    }
   }
   if (warp == 0) {
     if (lane < 12) reinterpret_cast<uint8_t*>(b.meta)[env * 16 + lane] = (uint8_t)d;
@@ -2061,8 +2081,8 @@ struct Launch {
       constexpr int MINB = 512 / M::NT;                       // 16 warps per SM at <= 128 registers
       auto kern = replay_reg_kernel<LOG2S, UC, MINB>;
       static SmemOptIn once;
-      if (int rc = ensure_smem(kern, M::XCHG_BYTES, once)) return rc;
-      kern<<<(unsigned)b.n_envs, M::NT, M::XCHG_BYTES, stream>>>(b, actions, act_f32, T, out, metric_every_step);
+      if (int rc = ensure_smem(kern, M::DYN_BYTES, once)) return rc;
+      kern<<<(unsigned)b.n_envs, M::NT, M::DYN_BYTES, stream>>>(b, actions, act_f32, T, out, metric_every_step);
       return (int)cudaGetLastError();
     } else if constexpr (STAGED && S >= 512 && QCD_REPLAY_CTA) {
       constexpr int RNT = (S / 2) < 256 ? (S / 2) : 256;
