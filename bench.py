@@ -250,6 +250,193 @@ def run_reference(args):
   return 0
 
 
+
+# ------------------------------------------------------------------------------------------------
+FP64_PEAK_FILE = os.path.join(ROOT, "MEASURED_PEAKS_FP64.json")       # committed copy of the gpurun measurement
+
+
+def load_fp64_peak():
+  """Measured DFMA peak of this pool's B200 (scripts/microbench_peaks.cu run under gpurun, committed)."""
+  try:
+    return float(json.load(open(FP64_PEAK_FILE))["fp64_dfma_tflops"]), "measured (MEASURED_PEAKS_FP64.json: scripts/microbench_peaks.cu on this pool's B200)"
+  except Exception:
+    return 37.1, "fallback (64 DFMA/clk/SM x 148 SMs x 1.965 GHz)"
+
+
+def tape_flops_per_env_step(tape_np, eta, S, metric_evals_per_env_step):
+  """Algorithmic FP64 flops per env-step of a tape: RX 6S, P 3S, CP 1.5S, CX 0 per gate,
+  8S per metric evaluation."""
+  g, w, c = (np.floor(tape_np[..., i]).astype(np.int64) for i in range(3))
+  same = w == c
+  per_gate = np.where(g == 0, np.where(same, 3.0, 1.5), np.where(g == 1, np.where(same, 6.0, 0.0), 0.0)) * S
+  return float(per_gate.mean() + 8.0 * S * metric_evals_per_env_step)
+
+
+def run_configs(args, torch, dist, dev, rank, world, stream):
+  """Short runs of BASELINE.json configs[0], [2], [3], [4]; each entry carries its own roofline and CPU port
+  rate.  configs[3] and [4] name a TOTAL number of envs, so they are strong-scaled (total / world per GPU)."""
+  from qcd_b200.batch import EnvBatch
+  from qcd_b200.targets import make_target
+  peak, peak_src = load_peaks()
+  out = {}
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+
+  def timed_ms(launch, k, w):
+    with torch.cuda.stream(stream):
+      for i in range(w):
+        launch(i)
+      stream.synchronize()
+      barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(stream)
+      for i in range(k):
+        launch(w + i)
+      e1.record(stream)
+      stream.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  def cpu(objective, eta, delta, tape_np, seconds):
+    if args.no_cpu or rank != 0:
+      return None
+    v, n, dt = cpu_port_steps_per_s(objective, eta, delta, tape_np, seconds, max_envs=16)
+    return {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first 16 envs, {n} env-steps in {dt:.1f} s, same action distribution (numpy restatement of env.py)"}
+
+  # ---- configs[2]: UC-toffoli, 65 536 envs per GPU, step kernel (weak scaling like the headline)
+  objective, eta, delta, N, _ = WORKLOADS['uc-toffoli']
+  target = make_target(objective, eta, seed=42)
+  S = 4 ** eta
+  Rr = 4                                                     # 4 x 108 MB of replicas > L2
+  bs = [EnvBatch(N, eta, delta, objective, target, device=dev) for _ in range(Rr)]
+  tape_np = make_tape(eta, TAPE_LEN, N, seed=4321 + rank)
+  tape = torch.as_tensor(tape_np, device=dev)
+  k3 = 400
+  ms = timed_ms(lambda i: bs[i % Rr].step(tape[i % TAPE_LEN]), k3, 40)
+  b_env = bs[0].algorithmic_bytes_per_step()
+  ach = b_env * N / (ms / k3 * 1e-3) / 1e9
+  out["uc-toffoli"] = {
+      "baseline_config": "configs[2]: UC-toffoli 3-qubit unitary composition, 65536 envs, max_depth=30",
+      "value": N * k3 * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "weak", "steps": k3,
+      "ms_per_step": ms / k3, "envs_per_gpu": N, "l2": f"{Rr} batch replicas round-robin (eager launches, PDL)",
+      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                   "kernel": "qcd::step_warp_kernel<log2S=6,UC>", "algorithmic_bytes_per_env_step": b_env,
+                   "peak_source": peak_src},
+      "cpu_baseline": cpu(objective, eta, delta, tape_np, 3.0)}
+  del bs, tape
+  torch.cuda.empty_cache()
+
+  # ---- configs[3]: SP-random eta=12, 1 Mi envs IN TOTAL sharded over the GPUs, punish=True, state-half observations
+  objective, eta, delta = 'SP-random', 12, 36
+  total = 1 << 20
+  N = total // world
+  S = 2 ** eta
+  free, _ = torch.cuda.mem_get_info(dev)
+  need = N * (16 * S + 8 * S + 256)
+  if free < need * 1.05:
+    out["sp-random12-1Mi"] = {"skipped": f"needs {need / 2**30:.0f} GiB per GPU, {free / 2**30:.0f} GiB free"}
+  else:
+    target = make_target(objective, eta, seed=42)
+    bt = EnvBatch(N, eta, delta, objective, target, punish=True, obs_mode='state', device=dev)
+    tape_np = make_tape(eta, 2, N, seed=777 + rank)
+    tape = torch.as_tensor(tape_np, device=dev)
+    k4 = 6
+    ms = timed_ms(lambda i: bt.step(tape[i % 2]), k4, 3)
+    b_env = bt.algorithmic_bytes_per_step()
+    ach = b_env * N / (ms / k4 * 1e-3) / 1e9
+    out["sp-random12-1Mi"] = {
+        "baseline_config": "configs[3]: SP-random max_qubits=12, 1M envs sharded over 1/2/4/8 B200, punish=True",
+        "value": total * k4 / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong", "steps": k4,
+        "ms_per_step": ms / k4, "envs_total": total, "envs_per_gpu": N, "max_depth": delta, "observations": "state",
+        "resident_gib_per_gpu": need / 2**30, "l2": "inputs (64 GiB / world of states) far larger than L2",
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "qcd::qcd_kernel<log2S=12,SP> (pair-streaming step)", "algorithmic_bytes_per_env_step": b_env,
+                     "peak_source": peak_src,
+                     "note": "algorithmic bytes count a full state write; stores of amplitudes a gate leaves untouched "
+                             "are skipped (ncu r01: real DRAM traffic = 0.83 x algorithmic), so frac can exceed 1"},
+        "cpu_baseline": cpu(objective, eta, delta, tape_np[:, :16], 3.0)}
+    del bt, tape
+    torch.cuda.empty_cache()
+
+  # ---- configs[4]: UC-random eta=6, 262 144 envs IN TOTAL, replay kernel, T = 64
+  objective, eta, delta = 'UC-random', 6, 24
+  total = 262144
+  N = total // world
+  S = 4 ** eta
+  target = make_target(objective, eta, seed=42)
+  br = EnvBatch(N, eta, delta, objective, target, obs_mode='state', device=dev)
+  tape_np = make_tape(eta, 2 * REPLAY_T, N, seed=999 + rank)
+  tape = torch.as_tensor(tape_np, device=dev)
+  k5 = 4
+  ms = timed_ms(lambda i: br.replay(tape[(i % 2) * REPLAY_T:(i % 2 + 1) * REPLAY_T]), k5, 2)
+  # metric evaluations of the last launch: finished episodes + the last step of envs that did not finish on it
+  br.zero_stats()
+  with torch.cuda.stream(stream):
+    br.replay(tape[:REPLAY_T])
+    stream.synchronize()
+  episodes = float(br.stats[0].item())
+  done_last = float(((br.terminated != 0) | (br.truncated != 0)).sum().item())
+  evals = (episodes + N - done_last) / (N * REPLAY_T)
+  flops = tape_flops_per_env_step(tape_np[:REPLAY_T], eta, S, evals)
+  rate = total * k5 * REPLAY_T / (ms * 1e-3)
+  fpeak, fsrc = load_fp64_peak()
+  ach = rate / world * flops / 1e12
+  out["uc-random6-replay"] = {
+      "baseline_config": "configs[4]: UC-random max_qubits=6 (64x64 unitary), 262144 envs, sequence-replay kernel",
+      "value": rate, "unit": UNIT, "n_gpus": world, "scaling": "strong", "steps": k5, "ms_per_step": ms / k5,
+      "envs_total": total, "envs_per_gpu": N, "steps_per_launch": REPLAY_T, "max_depth": delta,
+      "actions": "uniform-box (mean episode = 3 steps: a metric evaluation on every third step)",
+      "roofline": {"bound": "fp64", "achieved": ach, "peak": fpeak, "unit": "TFLOP/s", "frac": ach / fpeak, "traffic": None,
+                   "kernel": "qcd::replay_reg_kernel<log2S=12,UC>", "algorithmic_flops_per_env_step": flops,
+                   "metric_evaluations_per_env_step": evals, "peak_source": fsrc,
+                   "note": "state register-resident for the whole tape: HBM traffic is one state in/out per launch (3 % of "
+                           "the copy peak); FP64 is the only roofline left.  ncu (profiles/r02_summary.md): FP64 pipe 19 % "
+                           "active, issue slots 51 % - the kernel is issue/latency-bound by its control flow (per-step decode, "
+                           "depth bookkeeping, reset), not by DFMA throughput"},
+      "cpu_baseline": cpu(objective, eta, delta, tape_np[:, :16], 3.0)}
+  del br, tape
+  torch.cuda.empty_cache()
+
+  # ---- configs[0]: SP-bell, max_qubits=2, max_depth=12, ONE env through gym.make, random actions, reset on done
+  if rank == 0:
+    import qcd_gym
+    from qcd_b200 import gym_compat as gym
+    from oracle.qcd_oracle import OracleCircuitDesigner, sample_actions
+    qcd_gym.register_envs()
+    rng = np.random.default_rng(0)
+    acts = [sample_actions(rng, 2) for _ in range(4096)]
+    res = {}
+    for name, env in (("gpu", gym.make("CircuitDesigner-v0", max_qubits=2, max_depth=12, objective='SP-bell')),
+                      ("cpu_port", OracleCircuitDesigner(2, 12, 'SP-bell'))):
+      if name == "cpu_port" and args.no_cpu:
+        continue
+      env.reset()
+      for n in (2000, 20000):                                 # warm-up, then timed
+        t0 = time.perf_counter()
+        for i in range(n):
+          _, _, term, trunc, _ = env.step(acts[i & 4095])
+          if term or trunc:
+            env.reset()
+        dt = time.perf_counter() - t0
+      res[name] = n / dt
+    out["sp-bell-single-env"] = {
+        "baseline_config": "configs[0]: SP-bell, max_qubits=2, max_depth=12, single env, random actions",
+        "value": res["gpu"], "unit": "env-steps/s", "n_gpus": 1, "us_per_step": 1e6 / res["gpu"], "steps": 20000,
+        "api": "gym.make('CircuitDesigner-v0').step(action): numpy in / numpy out, one qcd_step1_sync call per step "
+               "(action as kernel argument, results written by the kernel into mapped pinned host memory)",
+        "cpu_baseline": None if "cpu_port" not in res else
+        {"value": res["cpu_port"], "unit": "env-steps/s", "cores": 1, "kind": "port",
+         "sample": "the same 20000 steps through oracle/qcd_oracle.py OracleCircuitDesigner"}}
+  barrier()
+  return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
   import torch
@@ -314,62 +501,82 @@ def run_native(args):
   # of G, one graph per remainder, so that EVERY timed launch is replayed from a graph.
   G = int(np.lcm(R, TAPE_LEN)) if mode == 'step' else R * 2
   stream = torch.cuda.Stream(dev)
+  side = torch.cuda.Stream(dev)
+  stat_buf = [torch.zeros(qlib.STATS_STRIDE, dtype=torch.float64, device=dev) for _ in range(2)]
   graphs = {}
 
-  def capture(n):
+  def capture(n, close):
+    """n consecutive launches; close=True appends the statistics fold that ends a reporting interval."""
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=stream):
       for i in range(n):
         launch(i)
+      if close:
+        probe.fold_stats(out=stat_buf[1], zero=True)
     return g
+
+  def plan(k):
+    """[(graph length, closes the interval)] covering k launches; the last graph also folds the statistics."""
+    lens = [G] * (k // G) + ([k % G] if k % G else [])
+    return [(n, i == len(lens) - 1) for i, n in enumerate(lens)]
 
   with torch.cuda.stream(stream):
     for i in range(max(W, 3)):
       launch(i)
+    probe.fold_stats(out=stat_buf[1], zero=True)     # (lazy module loading outside of any capture)
     stream.synchronize()
     if not args.no_graph:
-      for n in {G, K % G, W % G} - {0}:
-        if n <= max(K, W):
-          graphs[n] = capture(n)
-          graphs[n].replay()
+      for key in set(plan(K)) | set(plan(W)):
+        graphs[key] = capture(*key)
+        graphs[key].replay()
       stream.synchronize()
-  graph = graphs.get(G) or (next(iter(graphs.values())) if graphs else None)
+  graph = next(iter(graphs.values())) if graphs else None
 
   def run_steps(k):
-    done = 0
-    if G in graphs:
-      while done + G <= k:
-        graphs[G].replay()
-        done += G
-    if (k - done) in graphs:
-      graphs[k - done].replay()
-      done = k
-    while done < k:
-      launch(done)
-      done += 1
+    """k launches + the closing statistics fold, every kernel replayed from a CUDA graph; returns the graph lengths."""
+    if not graphs:
+      for i in range(k):
+        launch(i)
+      probe.fold_stats(out=stat_buf[1], zero=True)
+      return [0] * k
+    for key in plan(k):
+      graphs[key].replay()
+    return [n for n, _ in plan(k)]
 
+  # ---- the one collective of the path: the episode statistics of a reporting interval (96 B per rank), exchanged
+  # over NCCL/NVLink on a SIDE stream while the envs keep stepping (the reference only logs these numbers,
+  # algorithm.py:99-114).  Every interval ends with one small fold kernel (the 64 atomic-spreading replicas ->
+  # one vector, replicas cleared), captured as the last node of the interval's last graph.  Interval 0 = the
+  # warm-up: its vector is handed to the side stream right before the timed region starts, so its all-reduce
+  # runs while interval 1 (the K timed steps) executes; interval 1's vector is exchanged after the region.
   clocks = ClockSampler(local)
   with torch.cuda.stream(stream):
+    with torch.cuda.stream(side):                 # warm NCCL (communicator setup is lazy)
+      all_reduce_stats(torch.zeros(qlib.STATS_STRIDE, dtype=torch.float64, device=dev))
+    side.synchronize()
     run_steps(W)
-    # warm the (torch) reduction of the statistics replicas: its kernels are lazily loaded on first use
-    all_reduce_stats(shared_stats.sum(0))
+    stat_buf[0].copy_(stat_buf[1])                # interval 0's vector
     stream.synchronize()
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.start()
+    with torch.cuda.stream(side):
+      all_reduce_stats(stat_buf[0])               # in flight on the side stream during the timed region
     ev0.record(stream)
-    run_steps(K)
-    # the one collective of the path: episode statistics of all ranks (96 B) over NCCL/NVLink
-    stats = shared_stats.sum(0)          # all replicas of this rank accumulate into one vector
-    all_reduce_stats(stats)
+    graphs_used = run_steps(K)                    # K step launches + 1 fold, nothing else
     ev1.record(stream)
+    with torch.cuda.stream(side):
+      side.wait_event(ev1)
+      all_reduce_stats(stat_buf[1])
     stream.synchronize()
+    side.synchronize()
     clocks.stop()
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize(dev)
+  stats = stat_buf[1]
   elapsed_ms = ev0.elapsed_time(ev1)
   t_all = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
   if world > 1:
@@ -499,6 +706,14 @@ def run_native(args):
                         "[N, 4S], pitched D2H of the state half", "none": "no observations"}[e2e_obs]}
     del venv
 
+  # ---- the other BASELINE.json configs, short runs in the same job (driver-visible under `configs`)
+  configs = None
+  if args.workload == 'sp-ghz5' and not args.no_configs:
+    try: del batches, probe, tape
+    except NameError: pass
+    torch.cuda.empty_cache()
+    configs = run_configs(args, torch, dist, dev, rank, world, stream)
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -512,19 +727,11 @@ def run_native(args):
   else:   # replay: state in + out once per launch, actions per step, scalars once
     alg_bytes = N * (32 * S + (8 * S if obs_mode != 'none' else 0) + 96 + 16 * REPLAY_T)
   achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-  traffic = None
-  tpath = os.path.join(ROOT, "profiles", "traffic.json")
-  if os.path.exists(tpath):
-    try:
-      rec = json.load(open(tpath)).get(args.workload)
-      if isinstance(rec, dict):
-        traffic = int(rec["bytes"] * (N / rec["envs"]))
-    except Exception:
-      traffic = None
+  traffic = None      # DRAM bytes cannot be measured outside the profiler; the ncu figures are in profiles/r02_summary.md
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
               "traffic": traffic, "peak_source": peak_src, "kernel": "qcd::%s<log2S=%d,%s>" % (
                   ("step_warp_kernel" if S <= 128 else "qcd_kernel(pair-streaming step)") if mode == 'step' else
-                  ("replay_cta_kernel" if S >= 512 else "qcd_kernel(staged replay)"),
+                  ("replay_reg_kernel" if S >= 512 else "replay_warp_kernel"),
                   int(np.log2(S)), "UC" if 'UC' in objective else "SP"),
               "algorithmic_bytes_per_env_step": bytes_step_env, "launch_us": launch_ms * 1e3,
               "note": ("algorithmic bytes count a full state write; the kernels skip stores of amplitudes a "
@@ -552,10 +759,11 @@ def run_native(args):
                  "observations": obs_mode, "final_obs": bool(args.final_obs), "fused_stats": not args.no_stats,
                  "l2": f"{R} batch replicas stepped round-robin, footprint {R * footprint / 1e6:.0f} MB > L2 "
                        f"126 MB" if R > 1 else "single batch (no rotation)",
-                 "cuda_graph": graph is not None, "graph_len": G if graph is not None else 0,
+                 "cuda_graph": graph is not None, "graph_len": graphs_used if graph is not None else 0,
                  "steps_per_launch": steps_per_launch, "parallelism": f"env-sharded x{world}, stats all-reduce only"},
-      "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu,
+      "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": K + 1, "roofline": roofline, "cpu_baseline": cpu,
       "episode_stats": summarize(stats[:qlib.STATS_LEN]), "sweep": sweep, "device_loop": device_loop,
+      "configs": configs,
   }
   print(json.dumps(line), flush=True)
   if world > 1:
@@ -580,6 +788,7 @@ def main():
   ap.add_argument("--no-terminate", action="store_true", help="action tape without Terminate (episodes end by depth)")
   ap.add_argument("--no-sweep", action="store_true", help="skip the secondary 1 Mi-env measurement")
   ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE.json configs")
   ap.add_argument("--no-stats", action="store_true", help="do not accumulate episode statistics in the step kernel")
   ap.add_argument("--cpu-seconds", type=float, default=10.0)
   ap.add_argument("--e2e-steps", type=int, default=200)

@@ -165,7 +165,7 @@ int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int3
 int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream);
 
 /* Folds the QCD_STATS_COPIES replicas into out[QCD_STATS_STRIDE] (device, float64; entries >= QCD_STATS_LEN
- * are zero) with a one-warp kernel on `stream`, and clears the replicas when zero_raw != 0 (start of the
+ * are zero) with one small kernel on `stream`, and clears the replicas when zero_raw != 0 (start of the
  * next reporting interval).  `out` is what a rank hands to the statistics all-reduce (algorithm.py:99-114
  * only logs these numbers, so the exchange can run on a side stream while the envs keep stepping). */
 int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream);

@@ -2015,19 +2015,22 @@ stats_kernel(const qcd_batch_t b, double* __restrict__ stats) {
 }
 
 // Sum of the QCD_STATS_COPIES replicas of the statistics vector in a fixed order -> out[QCD_STATS_STRIDE];
-// optionally clears the replicas (start of the next reporting interval).  One warp.
-__global__ void __launch_bounds__(32)
+// optionally clears the replicas (start of the next reporting interval).  One CTA, one thread per replica
+// element (all loads in flight at once: a serial loop over the replicas costs 64 dependent L2 round trips).
+__global__ void __launch_bounds__(QCD_STATS_COPIES * QCD_STATS_STRIDE)
 fold_stats_kernel(double* __restrict__ raw, double* __restrict__ out, const int zero_raw) {
+  __shared__ double s_v[QCD_STATS_COPIES * QCD_STATS_STRIDE];
   pdl_wait();
-  const int k = threadIdx.x;
-  if (k >= QCD_STATS_STRIDE) return;
-  double acc = 0.0;
+  const int i = threadIdx.x;
+  s_v[i] = raw[i];
+  if (zero_raw) raw[i] = 0.0;
+  __syncthreads();
+  if (i < QCD_STATS_STRIDE) {
+    double acc = 0.0;
 #pragma unroll 8
-  for (int c = 0; c < QCD_STATS_COPIES; ++c) {
-    acc += raw[c * QCD_STATS_STRIDE + k];
-    if (zero_raw) raw[c * QCD_STATS_STRIDE + k] = 0.0;
+    for (int c = 0; c < QCD_STATS_COPIES; ++c) acc += s_v[c * QCD_STATS_STRIDE + i];
+    out[i] = i < QCD_STATS_LEN ? acc : 0.0;
   }
-  out[k] = k < QCD_STATS_LEN ? acc : 0.0;
 }
 
 #ifndef QCD_KERNELS_ONLY   // (a scratch translation unit may include this file for the kernels alone)
@@ -2240,8 +2243,15 @@ int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream) {
 
 int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream) {
   if (!stats_raw || !out) return QCD_E_NULL;
-  qcd::fold_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_raw, out, zero_raw);
-  return (int)cudaGetLastError();
+  // launched like qcd_step (programmatic stream serialization): its launch latency hides behind the tail of the
+  // step before it; griddepcontrol.wait at its top orders it after that step's statistics atomics
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1); cfg.blockDim = dim3(QCD_STATS_COPIES * QCD_STATS_STRIDE); cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = qcd::pdl_enabled() ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, qcd::fold_stats_kernel, stats_raw, out, zero_raw);
 }
 
 int qcd_step_sync(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream) {

@@ -51,13 +51,15 @@ __global__ void __launch_bounds__(256) ldsts_kernel(double* out, const int iters
   const int n = 4096;
   for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = make_double2(i, -i);
   __syncthreads();
+  volatile double2* vs = sm;                           // every access really goes to shared memory
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int j = (threadIdx.x + r * 256) & (n - 1);
-      double2 v = sm[j];
+      double2 v;
+      v.x = vs[j].x; v.y = vs[j].y;
       v.x += 1.0;
-      sm[j] = v;
+      vs[j].x = v.x; vs[j].y = v.y;
     }
   }
   __syncthreads();
@@ -112,7 +114,7 @@ int main() {
          "\"smem_lds128_gbs\": %.1f, \"smem_lds128_bytes_per_clk_per_sm\": %.1f, "
          "\"smem_lds_sts128_gbs\": %.1f, "
          "\"how\": \"dfma: 8 independent __fma_rn chains/thread, 8x256 threads/SM, best of 10 (2 flop per FMA); "
-         "smem: LDS.128 (and LDS.128+STS.128) conflict-free over 64 KiB, 3 CTAs x 256 threads/SM, best of 10; "
+         "smem: LDS.128 (and a volatile 64-bit load+store round trip) conflict-free over 64 KiB, 3 CTAs x 256 threads/SM, best of 10; "
          "per-clk figures use the cudaDevAttrClockRate clock\"}\n",
          p.name, sms, clk, tflops, fma / (ms_f * 1e-3) / ((double)clk * 1e3) / sms,
          lds_bytes / (ms_l * 1e-3) / 1e9, lds_bytes / (ms_l * 1e-3) / ((double)clk * 1e3) / sms,

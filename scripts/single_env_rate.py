@@ -21,3 +21,16 @@ for objective, eta, delta in (('SP-bell', 2, 12), ('UC-toffoli', 3, 30), ('SP-gh
         if term or trunc: env.reset()
       dt = time.perf_counter() - t0
     print(f"{objective} {name}: {n / dt:,.0f} steps/s ({dt / n * 1e6:.1f} us/step)", flush=True)
+
+# breakdown for SP-bell: the C call alone (launch + kernel + sync) vs the whole Python step
+import ctypes
+env = gym.make("CircuitDesigner-v0", max_qubits=2, max_depth=12, objective='SP-bell')
+env.reset()
+u = env.unwrapped
+act = (ctypes.c_double * 4)(1.0, 0.0, 0.0, 0.5)
+for n in (2000, 20000):
+  t0 = time.perf_counter()
+  for i in range(n):
+    u._batch.step1_sync(act, u._sptr)
+  dt = time.perf_counter() - t0
+print(f"SP-bell qcd_step1_sync alone: {dt / n * 1e6:.1f} us/call", flush=True)

@@ -48,7 +48,7 @@ def test_native_arm_needs_cuda():
 def test_native_arm_json_line_on_gpu(cuda_device):
   """The default workload with a short run: ONE JSON line carrying the contract's keys, a measured
   roofline against MEASURED_PEAKS.json, the CPU baseline, the end-to-end number and sane clocks."""
-  res = _run("--steps", "40", "--warmup", "5", "--cpu-seconds", "1", "--no-sweep", "--e2e-steps", "10", timeout=600)
+  res = _run("--steps", "40", "--warmup", "5", "--cpu-seconds", "1", "--no-sweep", "--e2e-steps", "10", timeout=900)
   assert res.returncode == 0, res.stderr[-2000:]
   lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
   assert len(lines) == 1
@@ -56,7 +56,8 @@ def test_native_arm_json_line_on_gpu(cuda_device):
   for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
     assert key in d, key
-  assert d["n_gpus"] == 1 and d["steps"] == 40 and d["gpu_launches"] == 40 and d["scaling"] == "weak"
+  assert d["n_gpus"] == 1 and d["steps"] == 40 and d["scaling"] == "weak"
+  assert d["gpu_launches"] == 40 + 1          # the timed steps + the statistics fold that closes the interval
   assert d["vs_baseline"] is None and d["data"] == "synthetic" and "SP-ghz5" in d["config"]["workload"]
   assert "model" not in d["config"] and d["config"]["cuda_graph"] is True
   r = d["roofline"]
@@ -67,4 +68,15 @@ def test_native_arm_json_line_on_gpu(cuda_device):
   assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 65536 * 16 and e["d2h_bytes_per_step"] > 65536 * 10
   c = d["cpu_baseline"]
   assert c["kind"] == "port" and c["cores"] == 1 and 0 < c["value"] < 1e6
+  # the other BASELINE.json configs ride in the same line, each with its own roofline
+  cf = d["configs"]
+  assert set(cf) == {"uc-toffoli", "sp-random12-1Mi", "uc-random6-replay", "sp-bell-single-env"}
+  assert cf["uc-toffoli"]["roofline"]["bound"] == "hbm" and 0.2 < cf["uc-toffoli"]["roofline"]["frac"] < 1.3
+  if "skipped" not in cf["sp-random12-1Mi"]:
+    assert cf["sp-random12-1Mi"]["scaling"] == "strong" and cf["sp-random12-1Mi"]["envs_total"] == 1 << 20
+    assert 0.5 < cf["sp-random12-1Mi"]["roofline"]["frac"] < 1.3
+  rp = cf["uc-random6-replay"]
+  assert rp["roofline"]["bound"] == "fp64" and rp["roofline"]["unit"] == "TFLOP/s" and 0 < rp["roofline"]["frac"] < 1
+  assert rp["envs_total"] == 262144 and rp["value"] > 1e8
+  assert cf["sp-bell-single-env"]["value"] > cf["sp-bell-single-env"]["cpu_baseline"]["value"]
   assert d["clocks"]["sm_max_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
