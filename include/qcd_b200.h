@@ -170,6 +170,14 @@ int qcd_reduce_stats(const qcd_batch_t* b, double* stats, void* stream);
  * only logs these numbers, so the exchange can run on a side stream while the envs keep stepping). */
 int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream);
 
+/* Rolling window of the most recent finished episodes, on the device: SB3's ep_info_buffer = deque(maxlen=100)
+ * of Monitor's info["episode"] records, which the reference's trainer averages (algorithm/algorithm.py:49,89-91,
+ * 100; monitor.py:37-48).  Call after a step: the episodes that finished in that step are appended in env order;
+ * ring is float64 [window][QCD_EP_FIELDS] = {r, l, d, o, q, m, c, env}, count[0] (int64, device) the number of
+ * episodes pushed so far (the newest is at row (count-1) % window). */
+#define QCD_EP_FIELDS 8
+int qcd_push_episodes(const qcd_batch_t* b, double* ring, int64_t* count, int32_t window, void* stream);
+
 /* qcd_step followed by cudaStreamSynchronize(stream) in one call: the single-env path (env.py:124-136 with
  * numpy in / numpy out), where the action and every output live in mapped pinned host memory. */
 int qcd_step_sync(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream);

@@ -53,7 +53,9 @@ class QcdHostOut(C.Structure):
               ("truncated", C.c_void_p), ("status", C.c_void_p), ("obs", C.c_void_p), ("obs_stride", C.c_int64)]
 
 
-EXPORTS = ("qcd_abi_version", "qcd_reset", "qcd_step", "qcd_replay", "qcd_reduce_stats", "qcd_fold_stats",
+EP_FIELDS = 8
+EP_NAMES = ("r", "l", "d", "o", "q", "m", "c", "env")
+EXPORTS = ("qcd_abi_version", "qcd_reset", "qcd_step", "qcd_replay", "qcd_reduce_stats", "qcd_fold_stats", "qcd_push_episodes",
            "qcd_step_sync", "qcd_step1_sync", "qcd_step_host")
 
 _lib = None
@@ -89,6 +91,8 @@ def load_library(path: str | None = None) -> C.CDLL:
   lib.qcd_reduce_stats.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p]
   lib.qcd_fold_stats.restype = C.c_int
   lib.qcd_fold_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+  lib.qcd_push_episodes.restype = C.c_int
+  lib.qcd_push_episodes.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
   lib.qcd_step_sync.restype = C.c_int
   lib.qcd_step_sync.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_int, C.c_void_p]
   lib.qcd_step1_sync.restype = C.c_int

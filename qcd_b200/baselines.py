@@ -66,11 +66,52 @@ def encode_circuit(gates, max_len: int) -> np.ndarray:
   return tape
 
 
+def gates_from_individual(solution, n_qubits: int | None = None, n_gates_per_qubit: int | None = None) -> list:
+  """Gate list of a GA individual, in the order the reference builds its QuantumCircuit from the gate grid.
+
+  `solution` is the individual's `n_qubits x n_gates_per_qubit` grid (or an object with `.solution`, `.n_qubits`,
+  `.n_gates_per_qubit`) of gate objects with `.name` in {'p','rx','cp','cx'}, `.parameters` and `.affected_qubits`
+  (cells may be None).  Mirrors `transform_to_executable_circuit`
+  (/root/reference/baselines/evo/individual.py:158-201): columns outer, qubits inner; a gate is emitted where its
+  cell is first met and the cells of the other qubits it touches in that column are skipped; the qiskit call is
+  `getattr(qc, name)(*parameters, *affected_qubits)`, i.e. `cx(control, target)`, `cp(theta, control, target)`,
+  `rx(theta, q)`, `p(theta, q)`.  Returns [(kind, wire, control, theta)] for `circuit_fitness` / `encode_circuit`."""
+  if hasattr(solution, 'solution'):
+    n_qubits = solution.n_qubits if n_qubits is None else n_qubits
+    n_gates_per_qubit = solution.n_gates_per_qubit if n_gates_per_qubit is None else n_gates_per_qubit
+    solution = solution.solution
+  n_qubits = len(solution) if n_qubits is None else n_qubits
+  n_gates_per_qubit = (len(solution[0]) if n_qubits else 0) if n_gates_per_qubit is None else n_gates_per_qubit
+  handled = [[False] * n_gates_per_qubit for _ in range(n_qubits)]
+  gates = []
+  for col in range(n_gates_per_qubit):
+    for q in range(n_qubits):
+      gate = solution[q][col]
+      if gate is None or handled[q][col]:
+        continue
+      qubits = [int(x) for x in gate.affected_qubits]
+      params = list(gate.parameters or [])
+      if gate.name in ('p', 'rx'):
+        gates.append((gate.name, qubits[0], qubits[0], float(params[0])))
+      elif gate.name == 'cp':
+        gates.append(('cp', qubits[1], qubits[0], float(params[0])))      # cp(theta, control, target)
+      elif gate.name == 'cx':
+        gates.append(('cx', qubits[1], qubits[0], None))                  # cx(control, target)
+      else:
+        raise ValueError(f"gate {gate.name!r} is not in the reference's gate set ['cx', 'rx', 'cp', 'p']")
+      if len(qubits) > 1:
+        for other in qubits:
+          if other != q:
+            handled[other][col] = True
+  return gates
+
+
 def circuit_fitness(objective: str, max_qubits: int, max_depth: int, circuits, target=None, seed=None,
                     penalize: bool = True, device=None) -> np.ndarray:
   """fitness(individual) of evo/run.py:25-31 for a population: R - penalize*C of each whole circuit.
 
-  circuits: list of gate lists [(kind in {'p','rx','cp','cx'}, wire, control, theta)].  One replay launch
+  circuits: list of gate lists [(kind in {'p','rx','cp','cx'}, wire, control, theta)] (see
+  `gates_from_individual` for GA individuals).  One replay launch
   applies every circuit from |0..0> / I and terminates it; the reward of the Terminate step is
   metric - cost (env.py:134-135 with sparse=True, punish=penalize)."""
   dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)

@@ -244,6 +244,12 @@ class EnvBatch:
     with torch.cuda.device(self.device):
       check(self.lib.qcd_reduce_stats(self._cref, self._stats_raw.data_ptr(), self._stream()), "qcd_reduce_stats")
 
+  def push_episodes(self, ring: torch.Tensor, count: torch.Tensor) -> None:
+    """Append the episodes that finished in the last step to the device ring (see `EpisodeWindow`)."""
+    with torch.cuda.device(self.device):
+      check(self.lib.qcd_push_episodes(self._cref, ring.data_ptr(), count.data_ptr(), int(ring.shape[0]), self._stream()),
+            "qcd_push_episodes")
+
   @property
   def stats(self) -> torch.Tensor:
     """float64 [QCD_STATS_LEN] running episode statistics (sum over the atomic-spreading copies)."""
@@ -264,6 +270,31 @@ class EnvBatch:
     return out
 
   # ------------------------------------------------------------------------------------------
+  # Checkpoint / resume of the environment state: everything a later `step` reads.
+  _STATE_KEYS = ('state', 'meta', 'last', 'ep_return', 'ep_length', 'episode_return', 'episode_length', 'reward',
+                 'metric', 'cost', 'depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status', 'obs',
+                 'final_obs', '_stats_raw')
+
+  def state_dict(self) -> dict:
+    """Host copies of every persistent buffer + the configuration they belong to (synchronises)."""
+    cfg = dict(num_envs=self.num_envs, max_qubits=self.qubits, max_depth=self.max_depth, objective=self.objective,
+               punish=self.punish, sparse=self.sparse, autoreset=self.autoreset, obs_mode=self.obs_mode)
+    bufs = {k: getattr(self, k).detach().cpu().clone() for k in self._STATE_KEYS if getattr(self, k) is not None}
+    return {'config': cfg, 'target': self.target.cpu().clone(), 'buffers': bufs}
+
+  def load_state_dict(self, sd: dict) -> None:
+    """Restore a `state_dict()` of a batch with the same configuration (shapes are checked)."""
+    mine = self.state_dict()['config']
+    if sd['config'] != mine:
+      raise ValueError(f"checkpoint is for {sd['config']}, this batch is {mine}")
+    if sd['target'].shape != self.target.shape or not torch.equal(sd['target'], self.target.cpu()):
+      raise ValueError("checkpoint was taken with another target")
+    for k, v in sd['buffers'].items():
+      dst = getattr(self, k)
+      if dst is None or dst.shape != v.shape or dst.dtype != v.dtype:
+        raise ValueError(f"buffer {k} does not match")
+      dst.copy_(v)
+
   def state_view(self) -> torch.Tensor:
     """complex128 [N,D] (SP) or [N,D,D] (UC) view of the resident states."""
     return self.state if self.kind == _lib.OBJ_SP else self.state.view(self.num_envs, self.dim, self.dim)
@@ -271,3 +302,47 @@ class EnvBatch:
   def algorithmic_bytes_per_step(self) -> int:
     """32*S state r/w + 8*S float32 observation + 96 B scalars."""
     return 32 * self.S + (8 * self.S if self.obs is not None else 0) + 96
+
+
+class EpisodeWindow:
+  """The most recent `window` finished episodes of a batch, on the device.
+
+  What SB3 keeps as `ep_info_buffer = deque(maxlen=100)` of Monitor's info["episode"] records and the reference's
+  trainer averages for its progress bar and the `return-100` / `length-100` curves
+  (/root/reference/algorithm/algorithm.py:49,89-91,100; monitor.py:37-48).  `push()` after every step is one small
+  launch, no synchronisation; `means()` / `episodes()` read the ring back."""
+
+  def __init__(self, batch: EnvBatch, window: int = 100):
+    if batch.host_outputs:
+      raise ValueError("EpisodeWindow reads device buffers; a host_outputs batch keeps its episode records on the host")
+    self.batch, self.window = batch, int(window)
+    self.ring = torch.zeros((self.window, _lib.EP_FIELDS), dtype=torch.float64, device=batch.device)
+    self.count = torch.zeros(1, dtype=torch.int64, device=batch.device)
+
+  def push(self) -> None:
+    self.batch.push_episodes(self.ring, self.count)
+
+  def reset(self) -> None:
+    self.ring.zero_(); self.count.zero_()
+
+  def episodes(self) -> list:
+    """Oldest -> newest list of {'r','l','d','o','q','m','c','env'} dicts (synchronises)."""
+    n = int(self.count.item())
+    rows = self.ring.cpu().numpy()
+    k = min(n, self.window)
+    order = [(n - k + i) % self.window for i in range(k)]
+    out = []
+    for j in order:
+      d = dict(zip(_lib.EP_NAMES, rows[j].tolist()))
+      for key in ('l', 'd', 'o', 'q', 'env'):
+        d[key] = int(d[key])
+      out.append(d)
+    return out
+
+  def means(self) -> dict:
+    """np.mean([ep[k] for ep in ep_info_buffer]) for k in r,l,d,o,q,m,c (synchronises); NaN while empty."""
+    n = min(int(self.count.item()), self.window)
+    if n == 0:
+      return {k: float('nan') for k in _lib.EP_NAMES[:7]}
+    m = self.ring[:n].mean(0).cpu().tolist() if n < self.window else self.ring.mean(0).cpu().tolist()
+    return dict(zip(_lib.EP_NAMES[:7], m[:7]))

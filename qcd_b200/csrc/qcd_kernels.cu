@@ -2033,6 +2033,57 @@ fold_stats_kernel(double* __restrict__ raw, double* __restrict__ out, const int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rolling window of the most recent finished episodes (SB3's ep_info_buffer = deque(maxlen=100) that the
+// reference's trainer averages: algorithm/algorithm.py:49,89-91,100), kept on the device.  The episodes that
+// finished in the LAST step are appended in env order (the order DummyVecEnv reports them); only the last
+// `window` of them are written, so the result does not depend on thread scheduling.  One CTA.
+//   ring[w][QCD_EP_FIELDS] = {r, l, d, o, q, m, c, env}   count[0] = episodes pushed so far
+__global__ void __launch_bounds__(1024)
+push_episodes_kernel(const qcd_batch_t b, double* __restrict__ ring, long long* __restrict__ count, const int window) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long N = b.n_envs;
+  auto finished = [&](const long env) {
+    return env < N && b.status[env] == QCD_ST_OK && (b.terminated[env] || b.truncated[env]);
+  };
+  // pass 1: how many episodes finished in this step
+  int mine = 0;
+  for (long env = tid; env < N; env += 1024) mine += finished(env);
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  if (lane == 0 && mine) atomicAdd(&s_total, mine);
+  __syncthreads();
+  const int total = s_total;
+  if (total == 0) return;
+  const long long base = count[0];
+  const int skip = total > window ? total - window : 0;       // older than the window: never stored
+  // pass 2: env-ordered rank of every finished episode (block scan per 1024 envs)
+  int before = 0;
+  for (long env0 = 0; env0 < N; env0 += 1024) {
+    const long env = env0 + tid;
+    const bool f = finished(env);
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, chunk = 0;
+    for (int wv = 0; wv < 32; ++wv) { const int c = s_warp[wv]; if (wv < warp) wbase += c; chunk += c; }
+    const int rank = before + wbase + __popc(bal & ((1u << lane) - 1u));
+    if (f && rank >= skip) {
+      double* row = ring + ((base + rank) % window) * QCD_EP_FIELDS;
+      row[0] = b.episode_return ? b.episode_return[env] : 0.0;
+      row[1] = b.episode_length ? (double)b.episode_length[env] : 0.0;
+      row[2] = (double)b.depth[env]; row[3] = (double)b.operations[env]; row[4] = (double)b.used_wires[env];
+      row[5] = b.metric[env]; row[6] = b.cost[env]; row[7] = (double)env;
+    }
+    before += chunk;
+    __syncthreads();
+  }
+  if (tid == 0) count[0] = base + total;
+}
+
 #ifndef QCD_KERNELS_ONLY   // (a scratch translation unit may include this file for the kernels alone)
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
@@ -2252,6 +2303,16 @@ int qcd_fold_stats(double* stats_raw, double* out, int zero_raw, void* stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = qcd::pdl_enabled() ? 1 : 0;
   return (int)cudaLaunchKernelEx(&cfg, qcd::fold_stats_kernel, stats_raw, out, zero_raw);
+}
+
+int qcd_push_episodes(const qcd_batch_t* b, double* ring, int64_t* count, int32_t window, void* stream) {
+  if (b && b->n_envs == 0) return 0;
+  int rc = qcd::validate(b, false, nullptr, QCD_ACT_F64);
+  if (rc) return rc;
+  if (!ring || !count) return QCD_E_NULL;
+  if (window < 1) return QCD_E_RANGE;
+  qcd::push_episodes_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*b, ring, reinterpret_cast<long long*>(count), window);
+  return (int)cudaGetLastError();
 }
 
 int qcd_step_sync(const qcd_batch_t* b, const void* actions, int action_dtype, void* stream) {

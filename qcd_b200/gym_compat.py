@@ -27,9 +27,16 @@ if HAVE_GYMNASIUM:                      # pragma: no cover
   registry = _gym.envs.registration.registry
   register = _gym.envs.registration.register
   make = _gym.make
+  make_vec = getattr(_gym, "make_vec", None)
   np_random = _gym.utils.seeding.np_random
   ResetNeeded = _gym.error.ResetNeeded
+  try:
+    VectorEnvBase = _gym.vector.VectorEnv
+  except Exception:
+    VectorEnvBase = object
 else:
+  VectorEnvBase = object                 # gymnasium.vector.VectorEnv when gymnasium is importable
+
 
   class ResetNeeded(Exception):
     """gymnasium.error.ResetNeeded"""
@@ -179,13 +186,31 @@ else:
       return self.env.reset(**kwargs)
 
   class _Spec:
-    def __init__(self, id, entry_point, kwargs):
+    def __init__(self, id, entry_point, kwargs, vector_entry_point=None):
       self.id, self.entry_point, self.kwargs = id, entry_point, dict(kwargs or {})
+      self.vector_entry_point = vector_entry_point
 
   registry: dict = {}
 
-  def register(id, entry_point, **kwargs):
-    registry[id] = _Spec(id, entry_point, kwargs.get('kwargs'))
+  def register(id, entry_point=None, vector_entry_point=None, **kwargs):
+    registry[id] = _Spec(id, entry_point, kwargs.get('kwargs'), vector_entry_point)
+
+  def _load(entry):
+    if isinstance(entry, str):
+      mod, attr = entry.split(':')
+      entry = getattr(importlib.import_module(mod), attr)
+    return entry
+
+  def make_vec(id, num_envs=1, **kwargs):
+    """gymnasium.make_vec for specs that carry a vector_entry_point."""
+    if id not in registry:
+      raise KeyError(f"Environment `{id}` is not registered")
+    spec = registry[id]
+    if spec.vector_entry_point is None:
+      raise KeyError(f"Environment `{id}` has no vector_entry_point")
+    env = _load(spec.vector_entry_point)(num_envs=num_envs, **{**spec.kwargs, **kwargs})
+    env.spec = spec
+    return env
 
   def make(id, **kwargs):
     if id not in registry:

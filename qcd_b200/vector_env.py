@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from .batch import EnvBatch
-from .gym_compat import Box, np_random
+from .gym_compat import Box, VectorEnvBase, np_random
 from .targets import make_target
 
 GATES = 3
@@ -29,13 +29,19 @@ def action_space_for(qubits: int) -> Box:
   return Box(np.array([0, 0, 0, -np.pi]), np.array([GATES - m, qubits - m, qubits - m, np.pi]))
 
 
-class CircuitDesignerVectorEnv:
+class CircuitDesignerVectorEnv(VectorEnvBase):
+  """A `gymnasium.vector.VectorEnv` (when gymnasium is importable) whose envs live in HBM; it is the
+  `vector_entry_point` of `CircuitDesigner-v0` (registration.py).  Observations, rewards and flags are torch
+  CUDA tensors; `step_host*` are the numpy-in / numpy-out variants."""
   metadata = {"render_modes": [], "autoreset_mode": "same_step"}
+  spec = None
+  render_mode = None
+  closed = False
 
   def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str,
                punish=True, sparse=True, seed=None, target=None, device=None,
                obs_mode: str = 'full', final_obs: bool = False, autoreset: bool = True,
-               raise_on_invalid: bool = False):
+               raise_on_invalid: bool = False, episode_window: int = 0, render_mode=None):
     self.num_envs = int(num_envs)
     self.qubits, self.depth = max_qubits, max_depth
     self.max_steps = max_depth * max_qubits * 2
@@ -60,6 +66,11 @@ class CircuitDesignerVectorEnv:
                             np.tile(self.single_action_space.high, (self.num_envs, 1)))
     self._host = None
     self._groups = None
+    # device-side rolling window of the last `episode_window` episodes (SB3 ep_info_buffer; algorithm.py:49,100)
+    self.window = None
+    if episode_window:
+      from .batch import EpisodeWindow
+      self.window = EpisodeWindow(self.batch, episode_window)
 
   # ------------------------------------------------------------------------------------------
   def _info(self) -> dict:
@@ -84,6 +95,8 @@ class CircuitDesignerVectorEnv:
     tensors (no allocation, no synchronisation): obs, reward f64, terminated, truncated, info."""
     b = self.batch
     b.step(actions)
+    if self.window is not None:
+      self.window.push()
     if self.raise_on_invalid and bool((b.status != 0).any()):
       bad = int(torch.nonzero(b.status)[0])
       raise AssertionError(f"env {bad}: invalid action {actions[bad].tolist()} (status {int(b.status[bad])})")
@@ -251,5 +264,15 @@ class CircuitDesignerVectorEnv:
       self.batch.zero_stats()
     return dict(zip(_lib.STAT_NAMES, vec.tolist()))
 
-  def close(self):
+  def rolling_means(self) -> dict:
+    """Means of r,l,d,o,q,m,c over the last `episode_window` finished episodes (the reference's `return-100`,
+    `length-100` and progress-bar numbers: algorithm.py:49,89-91,100).  Synchronises."""
+    if self.window is None:
+      raise RuntimeError("construct the env with episode_window=100")
+    return self.window.means()
+
+  def close(self, **kwargs):
+    self.closed = True
+
+  def close_extras(self, **kwargs):
     pass

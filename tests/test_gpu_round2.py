@@ -251,3 +251,84 @@ def test_single_env_zero_copy_outputs_are_fresh_arrays(cuda_device):
   o2 = env.step([0, 0, 0, np.pi / 2])[0]
   assert o0[0] == 1 and not np.array_equal(o1, o2) and not np.array_equal(o0, o1)
   np.testing.assert_allclose(o1[:8], [np.sqrt(.5), 0, 0, 0, 0, -np.sqrt(.5), 0, 0], atol=1e-7)
+
+
+def test_device_episode_window_matches_a_host_deque(cuda_device):
+  """episode_window=100 on the device == collections.deque(maxlen=100) of Monitor records fed in env order
+  (SB3 ep_info_buffer; algorithm.py:49,89-91,100)."""
+  from collections import deque
+  from qcd_b200 import CircuitDesignerVectorEnv
+  rng = np.random.default_rng(3)
+  N, eta, delta, T = 257, 3, 15, 40
+  venv = CircuitDesignerVectorEnv(N, eta, delta, 'SP-ghz3', episode_window=100)
+  ora = OracleBatch(N, eta, delta, 'SP-ghz3', venv.target)
+  venv.reset()
+  ref = deque(maxlen=100)
+  assert np.isnan(venv.rolling_means()['r'])
+  for t in range(T):
+    a = uniform_box_tape(rng, eta, 1, N, no_terminate=(t % 3 != 0))[0]
+    if t == 5: a[:, 0] = 2.5                       # 257 episodes finish in one step: only the last 100 may land
+    venv.step(torch.as_tensor(a, device=cuda_device)); ora.step(a)
+    for i in np.nonzero(ora.terminated | ora.truncated)[0]:
+      ref.append({'r': ora.episode_return[i], 'l': int(ora.episode_length[i]), 'd': int(ora.depth[i]), 'o': int(ora.operations[i]),
+                  'q': int(ora.used_wires[i]), 'm': ora.metric[i], 'c': ora.cost[i], 'env': int(i)})
+    if t in (2, 5, 6, T - 1):
+      got = venv.window.episodes()
+      assert len(got) == len(ref)
+      for g, r in zip(got, ref):
+        assert (g['env'], g['l'], g['d'], g['o'], g['q']) == (r['env'], r['l'], r['d'], r['o'], r['q'])
+        np.testing.assert_allclose([g['r'], g['m'], g['c']], [r['r'], r['m'], r['c']], atol=TOL, rtol=0)
+      means = venv.rolling_means()
+      for k in 'rldoqmc':
+        np.testing.assert_allclose(means[k], np.mean([e[k] for e in ref]), atol=1e-11, rtol=0)
+  assert int(venv.window.count.item()) == int(ora.stats[0])
+
+
+def test_env_state_checkpoint_round_trip(cuda_device):
+  """state_dict() / load_state_dict(): a restored batch continues bit-identically."""
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(14)
+  N, eta, delta = 300, 5, 20
+  target = make_target('SP-ghz5', eta)
+  a = EnvBatch(N, eta, delta, 'SP-ghz5', target, sparse=False, final_obs=True)
+  tape = torch.as_tensor(uniform_box_tape(rng, eta, 30, N), device=cuda_device)
+  for t in range(12): a.step(tape[t])
+  sd = a.state_dict()
+  b = EnvBatch(N, eta, delta, 'SP-ghz5', target, sparse=False, final_obs=True)
+  b.load_state_dict(sd)
+  for t in range(12, 30):
+    a.step(tape[t]); b.step(tape[t])
+  for k in EnvBatch._STATE_KEYS:
+    assert torch.equal(getattr(a, k), getattr(b, k)), k
+  with pytest.raises(ValueError):
+    EnvBatch(N, eta, delta + 1, 'SP-ghz5', target, sparse=False, final_obs=True).load_state_dict(sd)
+
+
+def test_make_vec_builds_the_batched_env(cuda_device):
+  import qcd_gym
+  from qcd_b200 import gym_compat as gym
+  from qcd_b200.vector_env import CircuitDesignerVectorEnv
+  qcd_gym.register_envs()
+  venv = gym.make_vec("CircuitDesigner-v0", num_envs=64, max_qubits=2, max_depth=12, objective='SP-bell')
+  assert isinstance(venv, CircuitDesignerVectorEnv) and venv.num_envs == 64 and venv.spec.id == "CircuitDesigner-v0"
+  obs, info = venv.reset()
+  assert obs.shape == (64, 16) and venv.single_action_space.shape == (4,)
+  a = torch.tensor([[1, 0, 0, np.pi / 2]] * 64, dtype=torch.float32, device=cuda_device)
+  obs, r, term, trunc, info = venv.step(a)
+  assert not bool(term.any()) and int(info['depth'].sum()) == 64
+
+
+def test_sb3_vec_env_rolling_window_and_zero_copy(cuda_device):
+  from qcd_b200.sb3_vec_env import CircuitDesignerSB3VecEnv
+  rng = np.random.default_rng(2)
+  n, eta, delta = 4, 2, 12
+  vec = CircuitDesignerSB3VecEnv(n, eta, delta, 'SP-bell', seed=1, stats_window_size=10)
+  vec.reset()
+  eps = []
+  for t in range(200):
+    obs, rew, dones, infos = vec.step(uniform_box_tape(rng, eta, 1, n)[0])
+    assert obs.shape == (n, 16) and rew.dtype == np.float32
+    eps += [i['episode'] for i in infos if 'episode' in i]
+  assert len(eps) > 20 and list(vec.ep_info_buffer) == eps[-10:]
+  np.testing.assert_allclose(vec.rolling_means()['m'], np.mean([e['m'] for e in eps[-10:]]))
+  assert sum(len(e.termination_reasons) for e in vec.envs) == len(eps)
