@@ -6,10 +6,11 @@
 //   qcd_kernel<!STAGED> K1b the same step for S >= 256: pair-streaming, one warp = one env per CTA.
 //   replay_warp_kernel K2a  T steps in one launch, S <= 256: the warp's tile stays in shared memory
 //                           (cp.async.bulk in / out).
-//   replay_cta_kernel  K2b  T steps in one launch, S >= 512: one CTA per env, 64 KiB of state in smem,
-//                           decode-ahead table, one barrier per step.
-//   qcd_kernel<STAGED>      first replay version; kept as the path for per-env targets.
-//   reset_kernel, stats_kernel
+//   replay_reg_kernel  K2b  T steps in one launch, S >= 512: one CTA per env, the state in REGISTERS (16
+//                           amplitudes per thread), gates by register arithmetic / shuffles, no barrier
+//                           inside the step loop, metric steps finalized per chunk.
+//   qcd_kernel<STAGED>      first replay version; kept as the S <= 256 path for per-env targets.
+//   reset_kernel, stats_kernel, fold_stats_kernel, push_episodes_kernel
 // One launch = one step (or one tape) of ALL envs; the step kernels are HBM-bound
 // (32*S + 8*S + ~96 bytes per env-step, S = 2^eta (SP) or 4^eta (UC) complex128 amplitudes).
 //
@@ -126,22 +127,6 @@ namespace qcd {
 #ifndef QCD_WARP_REPLAY_TILE_BYTES
 #define QCD_WARP_REPLAY_TILE_BYTES 8192 // state bytes per warp tile (ghz5: 16 envs)
 #endif
-#ifndef QCD_REPLAY_CTA
-#define QCD_REPLAY_CTA 1                // replay for S >= 512: CTA per env with decode-ahead (0: first version)
-#endif
-#ifndef QCD_REPLAY_IMPL
-#define QCD_REPLAY_IMPL 1               // replay for S >= 512: 1 register-resident (round 2), 0 shared-memory CTA kernel
-#endif
-#ifndef QCD_REPLAY_FUSE
-#define QCD_REPLAY_FUSE 1               // replay_cta_kernel: two consecutive gates per sweep over the state
-#endif
-#ifndef QCD_REPLAY_SPECIALISE
-#define QCD_REPLAY_SPECIALISE 1         // light+light fused sweeps compiled per pair of gate kinds
-#endif
-#ifndef QCD_REPLAY_MINB
-#define QCD_REPLAY_MINB 2               // CTAs/SM the 64-KiB replay kernel is compiled for (3 fit in smem but spill)
-#endif
-
 constexpr int K_NONE = 0, K_P = 1, K_RX = 2, K_CP = 3, K_CX = 4;
 constexpr int ACT_IMMEDIATE = 2;   // internal action mode of the step kernels: the (single) action is a kernel argument
 
@@ -338,77 +323,6 @@ __device__ __forceinline__ void apply_pair(const GateRec& g, int i0, double2& a0
       if ((i0 >> g.cbit) & 1) { const double2 t = a0; a0 = a1; a1 = t; }
       break;
     default: break;
-  }
-}
-
-// apply_pair with the gate kind known at compile time (no switch in the inner loops of the replay sweeps)
-template <int KIND>
-__device__ __forceinline__ void apply_pair_k(const GateRec& g, const int i0, double2& a0, double2& a1) {
-  if (KIND == K_P) {
-    a1 = mul_phase(a1, g.cr, g.sr);
-  } else if (KIND == K_CP) {
-    if ((i0 >> g.cbit) & 1) a1 = mul_phase(a1, g.cr, g.sr);
-  } else if (KIND == K_RX) {
-    const double2 n0 = rot_rx(a0, a1, g.cr, g.sr), n1 = rot_rx(a1, a0, g.cr, g.sr);
-    a0 = n0; a1 = n1;
-  } else if (KIND == K_CX) {
-    if ((i0 >> g.cbit) & 1) { const double2 t = a0; a0 = a1; a1 = t; }
-  }
-}
-
-// One sweep over a state in shared memory applying gate A then gate B (both "light": no metric, no
-// reset) to the 4 amplitudes closed under the two wire bits — or to the pair when the wires coincide.
-template <int KA, int KB>
-__device__ __forceinline__ void sweep_two_gates(double2* __restrict__ st, const int S, const int tid, const int nt,
-                                                const GateRec& gA, const GateRec& gB) {
-  if (gA.wbit == gB.wbit) {
-    const unsigned lowmask = (1u << gA.wbit) - 1u;
-    const int wb = 1 << gA.wbit;
-#pragma unroll 2
-    for (int k = tid; k < S / 2; k += nt) {
-      const int i0 = (int)((((unsigned)k & ~lowmask) << 1) | ((unsigned)k & lowmask));
-      double2 x0 = st[i0], x1 = st[i0 | wb];
-      apply_pair_k<KA>(gA, i0, x0, x1);
-      apply_pair_k<KB>(gB, i0, x0, x1);
-      st[i0] = x0; st[i0 | wb] = x1;
-    }
-  } else {
-    const int lo = gA.wbit < gB.wbit ? gA.wbit : gB.wbit, hi = gA.wbit < gB.wbit ? gB.wbit : gA.wbit;
-    const unsigned mlo = (1u << lo) - 1u, mhi = (1u << (hi - 1)) - 1u;
-    const int BA = 1 << gA.wbit, BB = 1 << gB.wbit;
-#pragma unroll 2
-    for (int q = tid; q < S / 4; q += nt) {
-      const unsigned q1 = (((unsigned)q & ~mhi) << 1) | ((unsigned)q & mhi);
-      const int i00 = (int)(((q1 & ~mlo) << 1) | (q1 & mlo));
-      double2 x00 = st[i00], xA = st[i00 | BA], xB = st[i00 | BB], xAB = st[i00 | BA | BB];
-      apply_pair_k<KA>(gA, i00, x00, xA);
-      apply_pair_k<KA>(gA, i00 | BB, xB, xAB);
-      apply_pair_k<KB>(gB, i00, x00, xB);
-      apply_pair_k<KB>(gB, i00 | BA, xA, xAB);
-      st[i00] = x00; st[i00 | BA] = xA; st[i00 | BB] = xB; st[i00 | BA | BB] = xAB;
-    }
-  }
-}
-
-template <int KA>
-__device__ __forceinline__ void sweep_two_gates_b(double2* st, const int S, const int tid, const int nt,
-                                                  const GateRec& gA, const GateRec& gB) {
-  switch (gB.kind) {
-    case K_P:  sweep_two_gates<KA, K_P>(st, S, tid, nt, gA, gB); break;
-    case K_RX: sweep_two_gates<KA, K_RX>(st, S, tid, nt, gA, gB); break;
-    case K_CP: sweep_two_gates<KA, K_CP>(st, S, tid, nt, gA, gB); break;
-    default:   sweep_two_gates<KA, K_CX>(st, S, tid, nt, gA, gB); break;
-  }
-}
-
-// both kinds in {P, RX, CP, CX}
-__device__ __forceinline__ void sweep_two_gates_dispatch(double2* st, const int S, const int tid, const int nt,
-                                                         const GateRec& gA, const GateRec& gB) {
-  switch (gA.kind) {
-    case K_P:  sweep_two_gates_b<K_P>(st, S, tid, nt, gA, gB); break;
-    case K_RX: sweep_two_gates_b<K_RX>(st, S, tid, nt, gA, gB); break;
-    case K_CP: sweep_two_gates_b<K_CP>(st, S, tid, nt, gA, gB); break;
-    default:   sweep_two_gates_b<K_CX>(st, S, tid, nt, gA, gB); break;
   }
 }
 
@@ -692,291 +606,10 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
   }
 }
 
-// env.py:106-114,133-135 + Monitor + per-step records of ONE env, by its control thread (replay kernels).
-template <bool UC>
-__device__ __forceinline__ void finalize_and_emit(const qcd_batch_t& b, const qcd_tape_out_t& out, EnvCtl& e,
-                                                  const int t, const int T, const long N, const long env,
-                                                  const bool want_metric, const double xa, const double xb,
-                                                  double* stats) {
-  const bool autoreset = b.flags & QCD_F_AUTORESET;
-  const bool done = (e.status == QCD_ST_OK) && (e.term || e.trunc);
-  e.cost_raw = depth_cost(b, e.depth);
-  const StepOut o = finalize_step<UC>(b, e, xa, xb, want_metric);
-  if (out.reward) out.reward[(long)t * N + env] = o.reward;
-  if (out.metric) out.metric[(long)t * N + env] = o.metric;
-  if (out.cost) out.cost[(long)t * N + env] = o.cost;
-  if (out.depth) out.depth[(long)t * N + env] = e.depth;
-  if (out.terminated) out.terminated[(long)t * N + env] = e.term;
-  if (out.truncated) out.truncated[(long)t * N + env] = e.trunc;
-  if (out.status) out.status[(long)t * N + env] = (int8_t)e.status;
-  if (t == T - 1) {
-    b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
-    b.depth[env] = e.depth; b.operations[env] = e.ops; b.used_wires[env] = e.used_cnt;
-    b.terminated[env] = e.term; b.truncated[env] = e.trunc; b.status[env] = (int8_t)e.status;
-  }
-  if (stats) {
-    if (e.status != QCD_ST_OK) atomicAdd(stats + QCD_STAT_BAD_ACTIONS, 1.0);
-    else atomicAdd(stats + QCD_STAT_STEPS, 1.0);
-  }
-  if (done) {
-    if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
-    if (stats) {
-      atomicAdd(stats + QCD_STAT_EPISODES, 1.0);
-      if (b.ep_return) { atomicAdd(stats + QCD_STAT_SUM_R, e.ep_ret); atomicAdd(stats + QCD_STAT_SUM_L, (double)e.ep_len); }
-      atomicAdd(stats + QCD_STAT_SUM_D, (double)e.depth); atomicAdd(stats + QCD_STAT_SUM_O, (double)e.ops);
-      atomicAdd(stats + QCD_STAT_SUM_Q, (double)e.used_cnt);
-      atomicAdd(stats + QCD_STAT_SUM_M, o.metric); atomicAdd(stats + QCD_STAT_SUM_C, o.cost);
-      atomicAdd(stats + (e.trunc ? QCD_STAT_N_DEPTH : QCD_STAT_N_DONE), 1.0);
-    }
-    if (autoreset) { e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2 for large states (S >= 512): one CTA per env, the state resident in shared memory for the whole
-// tape.  What made the first replay kernel slow was a per-step serial chain (one thread decoding an
-// action with a double-precision sincos while 255 waited, two CTA barriers per step).  Here
-//   * the part of the decode that depends on the action alone (floor, range checks, gate kind, sincos)
-//     is done for NT steps at once, one step per thread, into a table in smem (tape is known ahead);
-//   * the sequential bookkeeping (depth stack, ops, wires, truncation, auto-reset) is integer work and
-//     is replicated in EVERY thread, so nobody waits for a broadcast;
-//   * one CTA barrier per step (the butterflies of step t+1 read amplitudes other threads wrote in
-//     step t); the metric partial sums ride on that barrier (double-buffered by step parity) and are
-//     only computed on steps where the metric is needed (every step if dense / recorded, else done|last);
-//   * diagonal gates touch only the amplitudes they change (P: half, CP: a quarter), CX only swaps.
-struct __align__(16) StepRec { double cr, sr; int pk; int pad; };
-
-template <int LOG2S, bool UC, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-replay_cta_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_f32, const int T,
-                  const qcd_tape_out_t out, const int metric_every_step) {
-  constexpr int S = 1 << LOG2S, PPT = (S / 2) / NT, U = PPT < 4 ? PPT : 4;
-  static_assert(PPT >= 1, "replay_cta_kernel: at least one pair per thread");
-  extern __shared__ __align__(16) double2 s_state[];          // [S]
-  __shared__ StepRec s_tab[NT];
-  __shared__ double2 s_wred[2][NT / 32];
-
-  const int tid = threadIdx.x;
-  const long env = blockIdx.x;
-  const long N = b.n_envs;
-  const bool autoreset = b.flags & QCD_F_AUTORESET;
-  const int shift = UC ? b.n_qubits : 0;
-  double2* gstate = reinterpret_cast<double2*>(b.state) + env * S;
-  const double2* tgt = reinterpret_cast<const double2*>(b.target) + ((b.flags & QCD_F_TARGET_PER_ENV) ? env * S : 0);
-
-#pragma unroll 4
-  for (int i = tid; i < S; i += NT) s_state[i] = gstate[i];
-
-  EnvCtl e;
-  e.meta = reinterpret_cast<const uint4*>(b.meta)[env];      // every thread keeps the bookkeeping
-  e.last_m = 0; e.last_c = 0; e.ep_ret = 0; e.ep_len = 0;
-  if (tid == 0) {
-    if (b.last) { const double2 l2 = reinterpret_cast<const double2*>(b.last)[env]; e.last_m = l2.x; e.last_c = l2.y; }
-    if (b.ep_return) { e.ep_ret = b.ep_return[env]; e.ep_len = b.ep_length[env]; }
-  }
-  double* stats = stats_slice(b, env);
-  int par = 0;
-
-  for (int t0 = 0; t0 < T; t0 += NT) {
-    // ---- decode-ahead: step t0 + tid
-    if (t0 + tid < T) {
-      double a0, a1, a2, a3;
-      load_action(actions, act_f32, (long)(t0 + tid) * N + env, a0, a1, a2, a3);
-      const GateKind k = decode_kind(b.n_qubits, a0, a1, a2, a3);
-      StepRec r;
-      r.cr = k.cr; r.sr = k.sr; r.pad = 0;
-      r.pk = k.kind | (k.w << 3) | (k.c << 7) | (k.status << 11) | ((k.term ? 1 : 0) << 13);
-      s_tab[tid] = r;
-    }
-    __syncthreads();                                          // table (and, first time, the state) ready
-    const int nsteps = (T - t0) < NT ? (T - t0) : NT;
-    // thread 0: env.py:106-114,133-135 + Monitor + records of step t (uses e as booked for step t)
-    auto finalize0 = [&](const int t, const bool want_metric, const double xa, const double xb) {
-      finalize_and_emit<UC>(b, out, e, t, T, N, env, want_metric, xa, xb, stats);
-    };
-    auto unpack = [&](const StepRec& r, GateRec& g, int& status, bool& term, int& w, int& c) {
-      const int kind = r.pk & 7;
-      w = (r.pk >> 3) & 15; c = (r.pk >> 7) & 15; status = (r.pk >> 11) & 3; term = (r.pk >> 13) & 1;
-      g.cr = r.cr; g.sr = r.sr; g.kind = kind; g.wbit = w + shift; g.cbit = c + shift; g.flags = 0;
-    };
-    auto block_sums = [&](double ra, double rb) {            // warp partials ride on the step barrier
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        ra += __shfl_xor_sync(0xffffffffu, ra, off);
-        rb += __shfl_xor_sync(0xffffffffu, rb, off);
-      }
-      if ((tid & 31) == 0) s_wred[par][tid >> 5] = make_double2(ra, rb);
-    };
-    auto read_sums = [&](double& xa, double& xb) {
-      xa = 0.0; xb = 0.0;
-#pragma unroll
-      for (int wv = 0; wv < NT / 32; ++wv) { xa += s_wred[par][wv].x; xb += s_wred[par][wv].y; }
-    };
-
-#pragma unroll 1
-    for (int si = 0; si < nsteps;) {
-      const int t = t0 + si;
-      GateRec g;
-      int status, w, c;
-      bool term;
-      unpack(s_tab[si], g, status, term, w, c);
-      book_gate<false>(b, status, g.kind, w, c, term, e);     // identical in every thread (cost: thread 0)
-      const bool done = (status == QCD_ST_OK) && (e.term || e.trunc);
-      const bool reset = done && autoreset;
-      const bool want_metric = metric_every_step || done || t == T - 1;
-
-      if (QCD_REPLAY_FUSE && !want_metric && si + 1 < nsteps) {
-        // ---- fused pass: light step t (no metric, no reset) + step t+1 in ONE sweep over the state.
-        // Both gates are applied in registers to the 4 amplitudes closed under the two wire bits
-        // (or to the pair when the wires coincide / one step is a no-op).
-        if (tid == 0) finalize0(t, false, 0.0, 0.0);
-        GateRec g2;
-        int status2, w2, c2;
-        bool term2;
-        unpack(s_tab[si + 1], g2, status2, term2, w2, c2);
-        book_gate<false>(b, status2, g2.kind, w2, c2, term2, e);
-        const bool done2 = (status2 == QCD_ST_OK) && (e.term || e.trunc);
-        const bool reset2 = done2 && autoreset;
-        const bool want2 = metric_every_step || done2 || t + 1 == T - 1;
-        double ra = 0.0, rb = 0.0;
-        if (QCD_REPLAY_SPECIALISE && !want2 && !reset2 && g.kind != K_NONE && g2.kind != K_NONE) {
-          sweep_two_gates_dispatch(s_state, S, tid, NT, g, g2);   // light + light: kinds at compile time
-        } else if (g.kind == K_NONE || g2.kind == K_NONE || g.wbit == g2.wbit) {
-          const int wbit = (g.kind != K_NONE) ? g.wbit : g2.wbit;
-          const unsigned lowmask = (1u << wbit) - 1u;
-          const int wb = 1 << wbit;
-          if (g.kind != K_NONE || g2.kind != K_NONE || want2 || reset2) {
-#pragma unroll 2
-            for (int j = 0; j < PPT; ++j) {
-              const unsigned k = (unsigned)(tid + NT * j);
-              const int i0 = (int)(((k & ~lowmask) << 1) | (k & lowmask));
-              double2 x0 = s_state[i0], x1 = s_state[i0 | wb];
-              apply_pair(g, i0, x0, x1);
-              apply_pair(g2, i0, x0, x1);
-              if (want2) {
-                metric_acc<UC>(x0, __ldg(tgt + i0), ra, rb);
-                metric_acc<UC>(x1, __ldg(tgt + (i0 | wb)), ra, rb);
-              }
-              if (reset2) { x0 = reset_amp(UC, b.n_qubits, i0); x1 = reset_amp(UC, b.n_qubits, i0 | wb); }
-              s_state[i0] = x0; s_state[i0 | wb] = x1;
-            }
-          }
-        } else {
-          const int lo = g.wbit < g2.wbit ? g.wbit : g2.wbit, hi = g.wbit < g2.wbit ? g2.wbit : g.wbit;
-          const unsigned mlo = (1u << lo) - 1u, mhi = (1u << (hi - 1)) - 1u;   // masks on the compacted index
-          const int BA = 1 << g.wbit, BB = 1 << g2.wbit;
-#pragma unroll 2
-          for (int q = tid; q < S / 4; q += NT) {
-            const unsigned q1 = (((unsigned)q & ~mhi) << 1) | ((unsigned)q & mhi);   // zero at bit hi-1 ...
-            const int i00 = (int)(((q1 & ~mlo) << 1) | (q1 & mlo));                  // ... then at bit lo
-            double2 x00 = s_state[i00], xA = s_state[i00 | BA], xB = s_state[i00 | BB], xAB = s_state[i00 | BA | BB];
-            apply_pair(g, i00, x00, xA);
-            apply_pair(g, i00 | BB, xB, xAB);
-            apply_pair(g2, i00, x00, xB);
-            apply_pair(g2, i00 | BA, xA, xAB);
-            if (want2) {
-              metric_acc<UC>(x00, __ldg(tgt + i00), ra, rb);
-              metric_acc<UC>(xA, __ldg(tgt + (i00 | BA)), ra, rb);
-              metric_acc<UC>(xB, __ldg(tgt + (i00 | BB)), ra, rb);
-              metric_acc<UC>(xAB, __ldg(tgt + (i00 | BA | BB)), ra, rb);
-            }
-            if (reset2) {
-              x00 = reset_amp(UC, b.n_qubits, i00); xA = reset_amp(UC, b.n_qubits, i00 | BA);
-              xB = reset_amp(UC, b.n_qubits, i00 | BB); xAB = reset_amp(UC, b.n_qubits, i00 | BA | BB);
-            }
-            s_state[i00] = x00; s_state[i00 | BA] = xA; s_state[i00 | BB] = xB; s_state[i00 | BA | BB] = xAB;
-          }
-        }
-        if (want2) block_sums(ra, rb);
-        __syncthreads();
-        if (tid == 0) {
-          double xa = 0.0, xb = 0.0;
-          if (want2) read_sums(xa, xb);
-          finalize0(t + 1, want2, xa, xb);
-        }
-        if (reset2) e.meta = make_uint4(0, 0, 0, 0);
-        par ^= 1;
-        si += 2;
-        continue;
-      }
-
-      // ---- single-step pass
-      const unsigned lowmask = (1u << g.wbit) - 1u;
-      const int wb = 1 << g.wbit;
-      const int kind = g.kind;
-      double ra = 0.0, rb = 0.0;
-      if (want_metric) {
-#pragma unroll 1
-        for (int j0 = 0; j0 < PPT; j0 += U) {
-          int i0[U];
-          double2 x0[U], x1[U], t0v[U], t1v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const unsigned k = (unsigned)(tid + NT * (j0 + u));
-            i0[u] = (int)(((k & ~lowmask) << 1) | (k & lowmask));
-            x0[u] = s_state[i0[u]]; x1[u] = s_state[i0[u] | wb];
-            t0v[u] = __ldg(tgt + i0[u]); t1v[u] = __ldg(tgt + (i0[u] | wb));
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            apply_pair(g, i0[u], x0[u], x1[u]);
-            metric_acc<UC>(x0[u], t0v[u], ra, rb);
-            metric_acc<UC>(x1[u], t1v[u], ra, rb);
-            if (reset) { x0[u] = reset_amp(UC, b.n_qubits, i0[u]); x1[u] = reset_amp(UC, b.n_qubits, i0[u] | wb); }
-            if (kind != K_NONE || reset) { s_state[i0[u]] = x0[u]; s_state[i0[u] | wb] = x1[u]; }
-          }
-        }
-        block_sums(ra, rb);
-      } else if (kind != K_NONE) {                            // light path: touch only what changes
-#pragma unroll 4
-        for (int j = 0; j < PPT; ++j) {
-          const unsigned k = (unsigned)(tid + NT * j);
-          const int i0 = (int)(((k & ~lowmask) << 1) | (k & lowmask));
-          const bool cset = (i0 >> g.cbit) & 1;
-          if (kind == K_RX) {
-            const double2 a0 = s_state[i0], a1 = s_state[i0 | wb];
-            s_state[i0] = rot_rx(a0, a1, g.cr, g.sr);
-            s_state[i0 | wb] = rot_rx(a1, a0, g.cr, g.sr);
-          } else if (kind == K_P || (kind == K_CP && cset)) {
-            s_state[i0 | wb] = mul_phase(s_state[i0 | wb], g.cr, g.sr);
-          } else if (kind == K_CX && cset) {
-            const double2 a0 = s_state[i0], a1 = s_state[i0 | wb];
-            s_state[i0] = a1; s_state[i0 | wb] = a0;
-          }
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        double xa = 0.0, xb = 0.0;
-        if (want_metric) read_sums(xa, xb);
-        finalize0(t, want_metric, xa, xb);
-      }
-      if (reset) e.meta = make_uint4(0, 0, 0, 0);             // env.py:117-121, every thread's copy
-      par ^= 1;
-      si += 1;
-    }
-    __syncthreads();                                          // table may be overwritten by the next chunk
-  }
-
-  // ---- the state (and the observation of the last step) go back to HBM once
-  float* ob = b.obs ? b.obs + env * b.obs_stride : nullptr;
-#pragma unroll 4
-  for (int i = tid; i < S; i += NT) {
-    const double2 v = s_state[i];
-    gstate[i] = v;
-    if (ob) { ob[i] = (float)v.x; ob[S + i] = (float)v.y; }
-  }
-  if (tid == 0) {
-    reinterpret_cast<uint4*>(b.meta)[env] = e.meta;
-    if (b.last) reinterpret_cast<double2*>(b.last)[env] = make_double2(e.last_m, e.last_c);
-    if (b.ep_return) { b.ep_return[env] = e.ep_ret; b.ep_length[env] = e.ep_len; }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K2b, round 2: replay for S >= 512 with each env's state resident in REGISTERS for the whole tape.
 //
-// ncu on replay_cta_kernel (profiles/r01_summary.md §4): 4 695 warp-instructions per env-step = 73 per
+// ncu on the round-1 kernel (state in shared memory, one sweep and one barrier per gate; profiles/r01_summary.md §4): 4 695 warp-instructions per env-step = 73 per
 // amplitude pair where an RX pair needs ~14; the index arithmetic, the per-pair switch, the shared-memory
 // round trip of every sweep and the bookkeeping replicated in 256 threads were the cost, not FP64.  Here
 //   * a CTA of S/16 threads owns one env; every thread keeps 16 amplitudes (4 "local" index bits) in
@@ -2130,23 +1763,13 @@ struct Launch {
 
   static int run(const qcd_batch_t& b, const void* actions, int act_f32, int T,
                  const qcd_tape_out_t& out, int metric_every_step, cudaStream_t stream, const double4 imm) {
-    if constexpr (STAGED && S >= 512 && QCD_REPLAY_IMPL == 1) {
+    if constexpr (STAGED && S >= 512) {
       using M = RegMap<LOG2S, UC>;
       constexpr int MINB = 512 / M::NT;                       // 16 warps per SM at <= 128 registers
       auto kern = replay_reg_kernel<LOG2S, UC, MINB>;
       static SmemOptIn once;
       if (int rc = ensure_smem(kern, M::DYN_BYTES, once)) return rc;
       kern<<<(unsigned)b.n_envs, M::NT, M::DYN_BYTES, stream>>>(b, actions, act_f32, T, out, metric_every_step);
-      return (int)cudaGetLastError();
-    } else if constexpr (STAGED && S >= 512 && QCD_REPLAY_CTA) {
-      constexpr int RNT = (S / 2) < 256 ? (S / 2) : 256;
-      constexpr size_t smem = (size_t)S * sizeof(double2);
-      constexpr int MINB = S >= 4096 ? QCD_REPLAY_MINB : (S >= 2048 ? 4 : 6);   // smem allows 3 CTAs of 64 KiB
-      auto kern = replay_cta_kernel<LOG2S, UC, RNT, MINB>;
-      constexpr int BLOCK = RNT;
-      static SmemOptIn once;
-      if (int rc = ensure_smem(kern, smem, once)) return rc;
-      kern<<<(unsigned)b.n_envs, BLOCK, smem, stream>>>(b, actions, act_f32, T, out, metric_every_step);
       return (int)cudaGetLastError();
     } else if constexpr (STAGED && S <= 256 && QCD_REPLAY_WARP) {
       if (b.flags & QCD_F_TARGET_PER_ENV) return run_pair(b, actions, act_f32, T, out, metric_every_step, stream, imm);
