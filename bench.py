@@ -287,10 +287,12 @@ def run_configs(args, torch, dist, dev, rank, world, stream):
 
   def timed_ms(launch, k, w):
     with torch.cuda.stream(stream):
-      for i in range(w):
-        launch(i)
+      launch(0)                                   # (lazy loading / allocation before the barrier)
       stream.synchronize()
       barrier()
+      for i in range(w):                          # warm-up right before the timed launches (see run_native)
+        launch(i)
+      stream.synchronize()
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record(stream)
       for i in range(k):
@@ -549,26 +551,34 @@ def run_native(args):
   # one vector, replicas cleared), captured as the last node of the interval's last graph.  Interval 0 = the
   # warm-up: its vector is handed to the side stream right before the timed region starts, so its all-reduce
   # runs while interval 1 (the K timed steps) executes; interval 1's vector is exchanged after the region.
+  # Order: [setup, captures, NCCL warm-up] -> barrier + synchronize -> W untimed warm-up steps -> synchronize ->
+  # K timed steps -> synchronize + barrier.  The warm-up runs AFTER the barrier so that every rank enters the
+  # timed region straight from its warm-up (a GPU that idles at a barrier for milliseconds waiting for slower
+  # ranks starts its next kernels measurably slower; with 20 timed steps = 0.37 ms that decides the number).
   clocks = ClockSampler(local)
   with torch.cuda.stream(stream):
     with torch.cuda.stream(side):                 # warm NCCL (communicator setup is lazy)
       all_reduce_stats(torch.zeros(qlib.STATS_STRIDE, dtype=torch.float64, device=dev))
     side.synchronize()
-    run_steps(W)
-    stat_buf[0].copy_(stat_buf[1])                # interval 0's vector
     stream.synchronize()
+    clocks.start()                                # polling before, during and after the timed region
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize(dev)
+    run_steps(W)                                  # the W untimed warm-up steps (interval 0, closed by its fold)
+    stat_buf[0].copy_(stat_buf[1])                # interval 0's vector
+    stream.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.start()
-    with torch.cuda.stream(side):
-      all_reduce_stats(stat_buf[0])               # in flight on the side stream during the timed region
+    if args.exchange == "overlap":
+      with torch.cuda.stream(side):
+        all_reduce_stats(stat_buf[0])             # in flight on the side stream during the timed region
     ev0.record(stream)
     graphs_used = run_steps(K)                    # K step launches + 1 fold, nothing else
     ev1.record(stream)
     with torch.cuda.stream(side):
       side.wait_event(ev1)
+      if args.exchange != "overlap":
+        all_reduce_stats(stat_buf[0])
       all_reduce_stats(stat_buf[1])
     stream.synchronize()
     side.synchronize()
@@ -579,7 +589,11 @@ def run_native(args):
   stats = stat_buf[1]
   elapsed_ms = ev0.elapsed_time(ev1)
   t_all = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+  rank_ms = [elapsed_ms]
   if world > 1:
+    every = [torch.zeros_like(t_all) for _ in range(world)]
+    dist.all_gather(every, t_all)
+    rank_ms = [float(t.item()) for t in every]
     dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
   elapsed_ms = float(t_all.item())
   env_steps = N * K * steps_per_launch * world
@@ -760,7 +774,8 @@ def run_native(args):
                  "l2": f"{R} batch replicas stepped round-robin, footprint {R * footprint / 1e6:.0f} MB > L2 "
                        f"126 MB" if R > 1 else "single batch (no rotation)",
                  "cuda_graph": graph is not None, "graph_len": graphs_used if graph is not None else 0,
-                 "steps_per_launch": steps_per_launch, "parallelism": f"env-sharded x{world}, stats all-reduce only"},
+                 "steps_per_launch": steps_per_launch, "parallelism": f"env-sharded x{world}, stats all-reduce only",
+                 "stats_exchange": args.exchange, "rank_ms": [round(t, 5) for t in rank_ms]},
       "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": K + 1, "roofline": roofline, "cpu_baseline": cpu,
       "episode_stats": summarize(stats[:qlib.STATS_LEN]), "sweep": sweep, "device_loop": device_loop,
       "configs": configs,
@@ -782,6 +797,8 @@ def main():
   ap.add_argument("--obs", default="full", choices=["full", "state", "none"])
   ap.add_argument("--final-obs", action="store_true", help="also write terminal observations of finished envs")
   ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--exchange", default="overlap", choices=["overlap", "after"],
+                  help="statistics all-reduce of the previous interval: on a side stream during the timed region, or only after it")
   ap.add_argument("--actions-stable", action="store_true",
                   help="QCD_F_ACTIONS_STABLE: the tape is pre-generated, decode before griddepcontrol.wait")
   ap.add_argument("--no-rotate", action="store_true", help="single batch replica (L2-resident at small sizes)")

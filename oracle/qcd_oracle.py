@@ -12,12 +12,14 @@ What it restates
 * The arithmetic env.py reaches in the un-vendored third-party dependency
   `qiskit==1.0.2` (pinned at /root/reference/setup.py:14), restated from that release's
   published algorithm:
-    - `quantum_info.Operator._einsum_matmul`        -> `_einsum_matmul`
-    - `quantum_info.Statevector.from_instruction` /
-      `_evolve_operator` (start at e0, one einsum per gate, little-endian qargs)
+    - `quantum_info.Statevector.from_instruction` -> `_evolve_instruction` -> `_evolve_operator`
+      (start at e0; per gate: reshape to a rank-n tensor, TRANSPOSE the gate's axes to the front,
+      `np.dot(gate, .)`, transpose back; little-endian qargs)
                                                    -> `simulate_statevector`
+    - `quantum_info.Operator._einsum_matmul`        -> `_einsum_matmul`
     - `quantum_info.Operator(QuantumCircuit)` / `_append_instruction` / `compose`
-      (start at I, LEFT multiplication gate @ V)    -> `simulate_operator`
+      (start at I, LEFT multiplication gate @ V through `_einsum_matmul`)
+                                                   -> `simulate_operator`
     - `circuit.library.{PhaseGate,RXGate,CPhaseGate,CXGate,HGate,CCXGate}.__array__`
                                                    -> `gate_matrix`, `_H`, `_CCX`
     - `QuantumCircuit.depth / count_ops`, `circuit_to_dag(qc).idle_wires()`
@@ -93,16 +95,21 @@ def _einsum_matmul(tensor, mat, indices, shift=0, right_mul=False):
 
 
 def simulate_statevector(ops, n: int) -> np.ndarray:
-  """`Statevector.from_instruction(qc)`: e0, then per gate psi <- (G on qargs) psi (env.py:84,109)."""
+  """`Statevector.from_instruction(qc)` (env.py:84,109): e0, then per gate `Statevector._evolve_operator`
+  of qiskit 1.0.2 - NOT an einsum: the state is reshaped to (2,)*n, the gate's axes are transposed to the
+  front (`indices = [n-1-q for q in reversed(qargs)]`), contracted with `np.dot(gate, .)` as a
+  (2^k, 2^(n-k)) matrix, and transposed back."""
   psi = np.zeros(2 ** n, dtype=complex)
   psi[0] = 1.0
   for kind, qargs, theta in ops:
     g = gate_matrix(kind, theta)
-    k = len(qargs)
-    tensor = np.reshape(psi, (2,) * n)
-    mat = np.reshape(g, (2,) * (2 * k))
-    indices = [n - 1 - q for q in qargs]
-    psi = np.reshape(_einsum_matmul(tensor, mat, indices), 2 ** n)
+    indices = [n - 1 - q for q in reversed(qargs)]
+    axes = indices + [i for i in range(n) if i not in indices]
+    axes_inv = np.argsort(axes).tolist()
+    contract_dim = g.shape[1]
+    data = np.reshape(np.transpose(np.reshape(psi, (2,) * n), axes), (contract_dim, 2 ** n // contract_dim))
+    data = np.reshape(np.dot(g, data), (2,) * n)
+    psi = np.reshape(np.transpose(data, axes_inv), 2 ** n)
   return psi
 
 
