@@ -546,11 +546,14 @@ def run_native(args):
     return [n for n, _ in plan(k)]
 
   # ---- the one collective of the path: the episode statistics of a reporting interval (96 B per rank), exchanged
-  # over NCCL/NVLink on a SIDE stream while the envs keep stepping (the reference only logs these numbers,
-  # algorithm.py:99-114).  Every interval ends with one small fold kernel (the 64 atomic-spreading replicas ->
-  # one vector, replicas cleared), captured as the last node of the interval's last graph.  Interval 0 = the
-  # warm-up: its vector is handed to the side stream right before the timed region starts, so its all-reduce
-  # runs while interval 1 (the K timed steps) executes; interval 1's vector is exchanged after the region.
+  # over NCCL/NVLink on a SIDE stream, off the stepping stream's critical path (the reference only logs these
+  # numbers, algorithm.py:99-114).  Every interval ends with one small fold kernel (the 64 atomic-spreading
+  # replicas -> one vector, replicas cleared), captured as the last node of the interval's last graph.  Interval
+  # 0 = the warm-up, interval 1 = the K timed steps.  By default both vectors are all-reduced on the side stream
+  # right after the timed region; with --exchange overlap interval 0's all-reduce is in flight DURING the timed
+  # region (what a long-running trainer gets).  Measured on 8 GPUs: the concurrent NCCL kernel costs 2-3 of the 8
+  # ranks ~35 us once (bimodal per-rank times 0.372 / 0.408 ms), i.e. nothing for an interval of thousands of steps
+  # but 9 % of a 20-step region, which is why it is not the default of the 20-step protocol.
   # Order: [setup, captures, NCCL warm-up] -> barrier + synchronize -> W untimed warm-up steps -> synchronize ->
   # K timed steps -> synchronize + barrier.  The warm-up runs AFTER the barrier so that every rank enters the
   # timed region straight from its warm-up (a GPU that idles at a barrier for milliseconds waiting for slower
@@ -797,8 +800,9 @@ def main():
   ap.add_argument("--obs", default="full", choices=["full", "state", "none"])
   ap.add_argument("--final-obs", action="store_true", help="also write terminal observations of finished envs")
   ap.add_argument("--no-graph", action="store_true")
-  ap.add_argument("--exchange", default="overlap", choices=["overlap", "after"],
-                  help="statistics all-reduce of the previous interval: on a side stream during the timed region, or only after it")
+  ap.add_argument("--exchange", default="after", choices=["overlap", "after"],
+                  help="statistics all-reduce of the warm-up interval: after the timed region (default), or in flight on the "
+                       "side stream during it (measured on 8 GPUs: the NCCL kernel then costs some ranks ~35 us once)")
   ap.add_argument("--actions-stable", action="store_true",
                   help="QCD_F_ACTIONS_STABLE: the tape is pre-generated, decode before griddepcontrol.wait")
   ap.add_argument("--no-rotate", action="store_true", help="single batch replica (L2-resident at small sizes)")
