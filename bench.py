@@ -240,7 +240,12 @@ def run_reference(args):
       "data": "synthetic",
       "config": {"workload": f"{objective} eta={eta} max_depth={delta} envs={envs} (reference arm: "
                              f"{per_worker * cores}-env sample per step)", "actions": "uniform-box"},
-      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                       "per_core": value / cores,
+                       "per_core_note": "one process alone reaches ~14 k env-steps/s on this workload (the `cpu_baseline` "
+                                        "of the native arm); with one worker per logical core the per-core rate roughly "
+                                        "halves (SMT siblings, one IPC round trip per step), so this arm understates the "
+                                        "CPU by up to 2x"},
       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
       "note": "qiskit==1.0.2/gymnasium==0.29 are not installable in this image; the timed code is "
