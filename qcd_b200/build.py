@@ -29,14 +29,14 @@ def find_nvcc() -> str:
 
 
 def source_hash() -> str:
-  """sha256 over the sources, the header, the flags and QCD_NVCC_EXTRA (mtimes do not survive a copy of
-  the tree to another box; contents do)."""
+  """sha256 over the sources, the header and the base flags (mtimes do not survive a copy of the tree to
+  another box; contents do).  QCD_NVCC_EXTRA is deliberately not part of it: a library built with tuning
+  knobs stays valid for processes that do not carry the variable."""
   h = hashlib.sha256()
   for p in SOURCES + HEADERS:
     with open(p, "rb") as f:
       h.update(f.read())
   h.update(" ".join(NVCC_FLAGS[:-1]).encode())
-  h.update(os.environ.get("QCD_NVCC_EXTRA", "").encode())
   return h.hexdigest()
 
 

@@ -9,7 +9,7 @@ for line in open(sys.argv[2]):
         d=json.loads(line); print(tag, d['config']['workload'].split()[0], "%.3e"%d['value'], "frac=%.3f"%d['roofline']['frac'], "us=%.2f"%d['roofline']['launch_us'])
 PY
 }
-for v in "16 8" "20 8" "24 4" "28 2" "28 4" "18 8"; do
+for v in "20 8" "24 4" "28 2" "16 8"; do
   set -- $v
   QCD_NVCC_EXTRA="-DQCD_WARP_STEP_MINB=$1 -DQCD_WARP_PF_V1=$2" python -m qcd_b200.build > /dev/null 2>&1
   for steps in 20 2000; do
