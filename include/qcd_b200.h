@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define QCD_ABI_VERSION 5
+#define QCD_ABI_VERSION 6
 
 #define QCD_MAX_QUBITS_SP 12   /* S = 4096 complex128 = 64 KiB per env */
 #define QCD_MAX_QUBITS_UC 6    /* 64x64 unitary      = 64 KiB per env */
@@ -128,6 +128,8 @@ typedef struct qcd_tape_out {
   uint8_t* terminated;
   uint8_t* truncated;
   int8_t*  status;
+  int32_t* operations;      /* info['operations'] of every step */
+  int32_t* used_wires;      /* info['used_wires'] of every step */
 } qcd_tape_out_t;
 
 /* Episode statistics accumulated by qcd_reduce_stats: the Monitor fields of monitor.py:37-48 and the

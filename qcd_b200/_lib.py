@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 STATS_LEN = 12
 STATS_COPIES = 64
 STATS_STRIDE = 16
@@ -43,7 +43,8 @@ class QcdBatch(C.Structure):
 class QcdTapeOut(C.Structure):
   """Mirror of `qcd_tape_out_t`."""
   _fields_ = [("reward", C.c_void_p), ("metric", C.c_void_p), ("cost", C.c_void_p), ("depth", C.c_void_p),
-              ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("status", C.c_void_p)]
+              ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("status", C.c_void_p),
+              ("operations", C.c_void_p), ("used_wires", C.c_void_p)]
 
 
 class QcdHostOut(C.Structure):

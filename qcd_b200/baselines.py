@@ -1,7 +1,7 @@
 """Device-side drivers of the two non-RL baselines that call the hot path.
 
 random_baseline : /root/reference/plot/metrics.py:161-176 — per seed, 100 episodes of
-                  `env.step(env.action_space.sample())`, mean of the Monitor fields r,d,q,m,c.
+                  `env.step(env.action_space.sample())`, mean of the Monitor fields r,d,q,m,c: one replay launch.
 circuit_fitness : /root/reference/baselines/evo/run.py:17-33 — fitness of whole circuits of
                   cx/rx/cp/p gates: fidelity | similarity minus the depth cost, evaluated with the
                   replay kernel (one launch for the whole population).
@@ -28,29 +28,35 @@ def sample_actions(n: int, qubits: int, generator: torch.Generator, device) -> t
 def random_baseline(task: str, seeds: int = 8, episodes: int = 100, env_seed: int = 42, device=None) -> dict:
   """Means of Return/Depth/Qubits/Metric/Cost per seed for `task` = '<obj>-q<eta>-d<delta>'.
 
-  Every (seed, episode) pair is its own env: seeds*episodes envs are stepped in lock-step with
-  auto-reset off until all have finished (episodes are independent, so this is the same experiment as
-  the reference's sequential loop; the action streams differ from numpy's, the distribution does not)."""
+  Every (seed, episode) pair is its own env: the action tapes of all seeds*episodes envs are drawn on the
+  device and ONE `qcd_replay` launch (auto-reset off, per-step records) plays every episode to its end — no
+  Python loop over steps, no synchronisation per step; the Monitor fields of each env are then read at its first
+  finished step.  Episodes are independent, so this is the same experiment as the reference's sequential loop (the
+  action streams differ from numpy's, the distribution does not).  T = max_depth*max_qubits + 1 steps suffice: every
+  max_qubits gates raise the depth by at least one, and depth >= max_depth truncates (env.py:129)."""
   kw = parse_task(task)
   eta, delta, objective = kw['max_qubits'], kw['max_depth'], kw['objective']
   dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
   n = seeds * episodes
+  T = delta * eta + 1                                        # depth grows by >= 1 per eta gates: truncation by then
   batch = EnvBatch(n, eta, delta, objective, make_target(objective, eta, env_seed), autoreset=False, obs_mode='none',
                    track_episodes=True, fused_stats=False, device=dev)
   gens = [torch.Generator(device=dev).manual_seed(s + 1) for s in range(seeds)]
-  done = torch.zeros(n, dtype=torch.bool, device=dev)
-  out = {k: torch.zeros(n, dtype=torch.float64, device=dev) for k in 'rdqmc'}
-  for _ in range(delta * eta * 2 + 1):                       # env.py:37 max_steps bounds an episode
-    actions = torch.cat([sample_actions(episodes, eta, g, dev) for g in gens])
-    batch.step(actions)
-    fin = (batch.terminated.bool() | batch.truncated.bool()) & ~done
-    for k, src in zip('rdqmc', (batch.episode_return, batch.depth, batch.used_wires, batch.metric, batch.cost)):
-      out[k] = torch.where(fin, src.to(torch.float64), out[k])
-    done |= fin
-    if bool(done.all()):
-      break
-  names = {'r': 'Return', 'd': 'Depth', 'q': 'Qubits', 'm': 'Metric', 'c': 'Cost'}
-  return {names[k]: v.view(seeds, episodes).mean(1).cpu().numpy() for k, v in out.items()}
+  tape = torch.stack([torch.cat([sample_actions(episodes, eta, g, dev) for g in gens]) for _ in range(T)])   # [T,n,4]
+  f64, i32, u8 = torch.float64, torch.int32, torch.uint8
+  rec = {k: torch.zeros((T, n), dtype=dt, device=dev) for k, dt in
+         (('reward', f64), ('metric', f64), ('cost', f64), ('depth', i32), ('used_wires', i32), ('terminated', u8), ('truncated', u8))}
+  batch.replay(tape, rec)
+  done = (rec['terminated'] | rec['truncated']).bool()                                  # [T,n]
+  first = torch.argmax(done.to(torch.int8), dim=0)                                      # first finished step of each env
+  assert bool(done.any(0).all()), "an episode outlived max_depth*max_qubits+1 steps"
+  # Monitor's return = sum of the rewards up to and including the finishing step (monitor.py:35-37)
+  upto = torch.arange(T, device=dev)[:, None] <= first[None, :]
+  ret = (rec['reward'] * upto).sum(0)
+  pick = lambda t: t.gather(0, first[None, :])[0].to(f64)
+  out = {'Return': ret, 'Depth': pick(rec['depth']), 'Qubits': pick(rec['used_wires']), 'Metric': pick(rec['metric']),
+         'Cost': pick(rec['cost'])}
+  return {k: v.view(seeds, episodes).mean(1).cpu().numpy() for k, v in out.items()}
 
 
 GATE_CODES = {'p': 0, 'cp': 0, 'rx': 1, 'cx': 1}              # env.py:95-98: gate index of each kind

@@ -220,11 +220,12 @@ class EnvBatch:
   def replay(self, tape: torch.Tensor, record: dict | None = None) -> None:
     """T fused steps with the states resident in shared memory.  tape: [T,N,4] on device.
     record: optional dict of preallocated [T,N] tensors keyed by reward/metric/cost/depth/
-    terminated/truncated/status."""
+    terminated/truncated/status/operations/used_wires."""
     tape, code = self._action_arg(tape, (int(tape.shape[0]),))
     out = QcdTapeOut()
     want = {'reward': torch.float64, 'metric': torch.float64, 'cost': torch.float64, 'depth': torch.int32,
-            'terminated': torch.uint8, 'truncated': torch.uint8, 'status': torch.int8}
+            'terminated': torch.uint8, 'truncated': torch.uint8, 'status': torch.int8, 'operations': torch.int32,
+            'used_wires': torch.int32}
     for key, t in (record or {}).items():
       if key not in want:
         raise KeyError(key)

@@ -375,6 +375,8 @@ __device__ __forceinline__ void phase3(const qcd_batch_t& b, const qcd_tape_out_
     if (out.terminated) out.terminated[(long)t * N + cenv] = e.term;
     if (out.truncated) out.truncated[(long)t * N + cenv] = e.trunc;
     if (out.status) out.status[(long)t * N + cenv] = (int8_t)e.status;
+    if (out.operations) out.operations[(long)t * N + cenv] = e.ops;
+    if (out.used_wires) out.used_wires[(long)t * N + cenv] = e.used_cnt;
     if (t == T - 1) {
       b.reward[cenv] = o.reward; b.metric[cenv] = o.metric; b.cost[cenv] = o.cost;
       b.depth[cenv] = e.depth; b.operations[cenv] = e.ops; b.used_wires[cenv] = e.used_cnt;
@@ -886,6 +888,8 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         if (out.terminated) out.terminated[at] = term;
         if (out.truncated) out.truncated[at] = trunc;
         if (out.status) out.status[at] = (int8_t)status;
+        if (out.operations) out.operations[at] = (int)ops;
+        if (out.used_wires) out.used_wires[at] = __popc(used);
       }
       ep_len += ok;                                            // monitor.py:38 (every warp keeps its copy)
 
@@ -934,6 +938,8 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         if (out.terminated) out.terminated[at] = term;
         if (out.truncated) out.truncated[at] = trunc;
         if (out.status) out.status[at] = (int8_t)status;
+        if (out.operations) out.operations[at] = mi.z;
+        if (out.used_wires) out.used_wires[at] = used_cnt;
         if (t == T - 1) {
           b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
           b.depth[env] = depth; b.operations[env] = mi.z; b.used_wires[env] = used_cnt;
@@ -1370,7 +1376,7 @@ step_warp_kernel(const qcd_batch_t b, const void* __restrict__ actions, const in
   // ---- finalize + scalar outputs + fused statistics
   pdl_launch_dependents();                        // the next step's grid may start its scalar phase now
                                                   // (triggering at kernel entry measured 2 % slower)
-  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   phase3<UC, 32>(b, none, e, ctl, env, 0, 1, N, lane, mysum, ctl, stats_slice(b, tile));
   if (ctl) {
     reinterpret_cast<uint4*>(b.meta)[env] = e.meta;
@@ -1886,7 +1892,7 @@ int qcd_step(const qcd_batch_t* b, const void* actions, int action_dtype, void* 
   if (b && b->n_envs == 0) return 0;          // empty batch: nothing to do
   int rc = qcd::validate(b, true, actions, action_dtype);
   if (rc) return rc;
-  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   return qcd::dispatch<false>(*b, actions, action_dtype == QCD_ACT_F32, 1, none, 1, (cudaStream_t)stream);
 }
 
@@ -1896,7 +1902,7 @@ int qcd_replay(const qcd_batch_t* b, const void* actions, int action_dtype, int3
   int rc = qcd::validate(b, true, actions, action_dtype);
   if (rc) return rc;
   if (n_steps < 1) return QCD_E_RANGE;
-  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const qcd_tape_out_t o = out ? *out : none;
   // info['metric'] is defined on every step (env.py:133); it is only *needed* on every step when
   // someone records it or when the reward is dense.
@@ -1949,7 +1955,7 @@ int qcd_step1_sync(const qcd_batch_t* b, const double* action, void* stream) {
   if (rc) return rc;
   if (!action) return QCD_E_NULL;
   if (b->n_envs != 1) return QCD_E_RANGE;
-  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const qcd_tape_out_t none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const double4 imm = {action[0], action[1], action[2], action[3]};      // travels as a kernel argument
   rc = qcd::dispatch<false>(*b, nullptr, qcd::ACT_IMMEDIATE, 1, none, 1, (cudaStream_t)stream, imm);
   if (rc) return rc;

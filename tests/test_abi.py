@@ -33,7 +33,7 @@ def test_struct_layout_matches_c():
   # 6 int32 + 2 double + 1 int64 + 20 pointers, natural alignment, no padding surprises
   assert C.sizeof(_lib.QcdBatch) == 6 * 4 + 2 * 8 + 8 + 20 * 8
   assert _lib.QcdBatch.state.offset == 48 and _lib.QcdBatch.obs_stride.offset == 40
-  assert C.sizeof(_lib.QcdTapeOut) == 7 * 8
+  assert C.sizeof(_lib.QcdTapeOut) == 9 * 8
 
 
 def test_argument_validation_without_gpu(lib):

@@ -117,11 +117,12 @@ def test_replay_equals_repeated_steps(cuda_device, objective, eta, delta, sparse
   tape = torch.as_tensor(uniform_box_tape(rng, eta, T, N), device=cuda_device)
   rec = {k: torch.zeros((T, N), dtype=dt, device=cuda_device) for k, dt in
          [('reward', torch.float64), ('metric', torch.float64), ('cost', torch.float64), ('depth', torch.int32),
-          ('terminated', torch.uint8), ('truncated', torch.uint8), ('status', torch.int8)]}
+          ('terminated', torch.uint8), ('truncated', torch.uint8), ('status', torch.int8),
+          ('operations', torch.int32), ('used_wires', torch.int32)]}
   b.replay(tape, rec)
   # amplitudes and integers are bit-identical (same explicitly rounded gate arithmetic in every
   # kernel); metric-derived floats may differ in the last bits (different reduction trees).
-  exact = ('depth', 'terminated', 'truncated', 'status')
+  exact = ('depth', 'terminated', 'truncated', 'status', 'operations', 'used_wires')
   def same(x, y, name):
     if name in exact or not x.dtype.is_floating_point:
       assert torch.equal(x, y), name
