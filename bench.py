@@ -334,6 +334,7 @@ def run_configs(args, torch, dist, dev, rank, world, stream):
       "ms_per_step": ms / k3, "envs_per_gpu": N, "l2": f"{Rr} batch replicas round-robin (eager launches, PDL)",
       "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                    "kernel": "qcd::step_warp_kernel<log2S=6,UC>", "algorithmic_bytes_per_env_step": b_env,
+                   "modelled_dram_bytes_per_env_step": modelled_dram_bytes_per_env_step(tape_np, eta, S, True, 8 * S),
                    "peak_source": peak_src},
       "cpu_baseline": cpu(objective, eta, delta, tape_np, 3.0)}
   del bs, tape
@@ -364,6 +365,8 @@ def run_configs(args, torch, dist, dev, rank, world, stream):
         "resident_gib_per_gpu": need / 2**30, "l2": "inputs (64 GiB / world of states) far larger than L2",
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "kernel": "qcd::qcd_kernel<log2S=12,SP> (pair-streaming step)", "algorithmic_bytes_per_env_step": b_env,
+                     "modelled_dram_bytes_per_env_step": modelled_dram_bytes_per_env_step(tape_np, eta, S, False, 8 * S),
+                     "frac_of_modelled_traffic": modelled_dram_bytes_per_env_step(tape_np, eta, S, False, 8 * S) / b_env * ach / peak,
                      "peak_source": peak_src,
                      "note": "algorithmic bytes count a full state write; stores of amplitudes a gate leaves untouched "
                              "are skipped (ncu r01: real DRAM traffic = 0.83 x algorithmic), so frac can exceed 1"},
@@ -442,6 +445,24 @@ def run_configs(args, torch, dist, dev, rank, world, stream):
          "sample": "the same 20000 steps through oracle/qcd_oracle.py OracleCircuitDesigner"}}
   barrier()
   return out
+
+
+def modelled_dram_bytes_per_env_step(tape_np, eta, S, uc, obs_bytes):
+  """Bytes one env-step really moves to/from DRAM under a 32-byte-sector model of the step kernels, which only store
+  the amplitudes a gate changed: state read 16S, state write = the sectors holding changed amplitudes (RX all, P / CX
+  half or all depending on whether the bit is bit 0 of the flat index, CP a quarter or half, Terminate + auto-reset
+  all), the float32 state half of the observation, and 150 B of scalars.  A model, not a measurement (truncation
+  resets are not counted); the ncu figures are in profiles/."""
+  g, w, c = (np.floor(tape_np[..., i]).astype(np.int64) for i in range(3))
+  shift = eta if uc else 0
+  wb, cb = w + shift, c + shift
+  same = w == c
+  full, half, quarter = 16.0 * S, 8.0 * S, 4.0 * S
+  p_w = np.where(wb == 0, full, half)
+  cp_w = np.where(np.minimum(wb, cb) == 0, half, quarter)
+  cx_w = np.where(cb == 0, full, half)
+  state_w = np.where(g == 2, full, np.where(g == 0, np.where(same, p_w, cp_w), np.where(same, full, cx_w)))
+  return float(16.0 * S + state_w.mean() + obs_bytes + 150.0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -749,6 +770,7 @@ def run_native(args):
   else:   # replay: state in + out once per launch, actions per step, scalars once
     alg_bytes = N * (32 * S + (8 * S if obs_mode != 'none' else 0) + 96 + 16 * REPLAY_T)
   achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+  modelled = modelled_dram_bytes_per_env_step(tape_np, eta, S, 'UC' in objective, 8 * S if obs_mode != 'none' else 0)
   traffic = None      # DRAM bytes cannot be measured outside the profiler; the ncu figures are in profiles/r02_summary.md
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
               "traffic": traffic, "peak_source": peak_src, "kernel": "qcd::%s<log2S=%d,%s>" % (
@@ -756,8 +778,11 @@ def run_native(args):
                   ("replay_reg_kernel" if S >= 512 else "replay_warp_kernel"),
                   int(np.log2(S)), "UC" if 'UC' in objective else "SP"),
               "algorithmic_bytes_per_env_step": bytes_step_env, "launch_us": launch_ms * 1e3,
-              "note": ("algorithmic bytes count a full state write; the kernels skip stores of amplitudes a "
-                       "gate leaves untouched (P/CP/CX/Terminate), so frac can read slightly above 1") if mode == 'step'
+              "modelled_dram_bytes_per_env_step": modelled if mode == 'step' else None,
+              "frac_of_modelled_traffic": (modelled * N / (launch_ms * 1e-3) / 1e9 / peak) if mode == 'step' else None,
+              "note": ("`achieved` uses SURVEY 8(d)'s algorithmic bytes, which count a full state write; the kernels skip "
+                       "stores of amplitudes a gate leaves untouched, so frac can read above 1 at large S.  "
+                       "`modelled_dram_bytes_per_env_step` is what a 32-byte-sector model says really moves") if mode == 'step'
               else ("replay keeps the state in shared memory for the whole tape: HBM traffic is one state in/out "
                     "per launch, the kernel is instruction-issue bound (ncu: profiles/r01_summary.md), so the "
                     "HBM fraction is low by construction")}
