@@ -669,8 +669,10 @@ struct RegMap {
   static constexpr size_t DYN_BYTES = XCHG_BYTES + TGT_BYTES;
 };
 
-struct __align__(16) RegStep { double cr, sr; int pk; int pad; };
-// pk: [2:0] kind [4:3] status [5] term [9:6] w [13:10] c [17:14] target position [21:18] control position
+struct __align__(16) RegStep { double cr, sr; int pk; int aux; };
+// pk: [2:0] kind [4:3] status [5] term [9:6] w [13:10] c [17:14] target position [21:18] control position [22] metric
+// needed whatever happens;  aux: [15:0] the 16 register slots the CONTROL allows (all for P / RX, the slots with
+// the control's register bit set for CP / CX, 0 = the control is a thread bit: decided per thread) [27:16] wire mask
 
 // slots k (of 16) whose bit j is set: 0xAAAA, 0xCCCC, 0xF0F0, 0xFF00
 __device__ __forceinline__ unsigned local_mask(const int j) { return (unsigned)(0xFF00F0F0CCCCAAAAull >> (16 * j)) & 0xffffu; }
@@ -728,7 +730,6 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   const long N = b.n_envs;
   const bool autoreset = b.flags & QCD_F_AUTORESET;
   const int shift = UC ? b.n_qubits : 0;
-  const int max_ops = b.max_depth * b.n_qubits * 2;
   const unsigned tpat = (unsigned)tid << 4;                   // bit p (p >= 4) = this thread's bit at position p
   int tbase = 0;
 #pragma unroll
@@ -773,10 +774,12 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       load_action(actions, act_f32, (long)(t0 + i) * N + env, a0, a1, a2, a3);
       const GateKind k = decode_kind(b.n_qubits, a0, a1, a2, a3);
       RegStep r;
-      r.cr = k.cr; r.sr = k.sr; r.pad = 0;
+      r.cr = k.cr; r.sr = k.sr;
       int tpos = (int)((POS >> (4 * (k.w + shift))) & 15ull), cpos = (int)((POS >> (4 * (k.c + shift))) & 15ull);
       // CP is symmetric in its two qubits: let the REGISTER-resident one play the target
       if (k.kind == K_CP && tpos >= 4 && cpos < 4) { const int x = tpos; tpos = cpos; cpos = x; }
+      const bool controlled = k.kind == K_CP || k.kind == K_CX;
+      r.aux = (int)(!controlled ? 0xffffu : (cpos < 4 ? local_mask(cpos) : 0u)) | (((1 << k.w) | (1 << k.c)) << 16);
       // bit 22: the metric of this step is needed whatever happens (recorded / dense reward / last step)
       r.pk = k.kind | (k.status << 3) | ((k.term ? 1 : 0) << 5) | (k.w << 6) | (k.c << 10) | (tpos << 14) | (cpos << 18) |
              ((metric_every_step || t0 + i == T - 1) ? (1 << 22) : 0);
@@ -791,6 +794,7 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
 #pragma unroll 1
     for (int si = 0; si < nsteps; ++si) {
       const double cr = s_tab[si].cr, sr = s_tab[si].sr;
+      const int aux = s_tab[si].aux;
       const int pk = n_pk;
       const int kind = pk & 7;
       n_pk = s_tab[si + 1 < nsteps ? si + 1 : si].pk;
@@ -802,16 +806,15 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         const int lvl = min(max(dw, dc) + 1, 255);             // saturate (only past truncation)
         if (lane == w || lane == c) d = lvl;
         ops = min(ops + 1u, 0xffffu);
-        used |= (1u << w) | (1u << c);
+        used |= (unsigned)aux >> 16;
       }
       const int depth = __reduce_max_sync(FULL, d);
 
       if (kind != K_NONE) {
         const int tpos = (pk >> 14) & 15, cpos = (pk >> 18) & 15;
-        // slots (of 16) this gate touches as far as the CONTROL is concerned: all of them for P / RX
-        unsigned cmask = 0xffffu;
-        if (kind == K_CP || kind == K_CX)
-          cmask = cpos < 4 ? local_mask(cpos) : (((tpat >> cpos) & 1u) ? 0xffffu : 0u);
+        // slots (of 16) this gate touches as far as the CONTROL is concerned (decoded ahead; 0 = thread-bit control)
+        unsigned cmask = (unsigned)aux & 0xffffu;
+        if (cmask == 0u) cmask = ((tpat >> cpos) & 1u) ? 0xffffu : 0u;
         if (tpos < 4) {
           switch (tpos) {
             case 0: reg_gate_local<0>(kind, cmask, cr, sr, a); break;
@@ -854,7 +857,9 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       const int status = (pk >> 3) & 3;
       const bool term = (pk >> 5) & 1;
       const bool ok = status == QCD_ST_OK;
-      const bool trunc = ok && (depth >= b.max_depth || (int)ops >= max_ops);
+      // env.py:129 also truncates at operations >= max_depth*max_qubits*2; every layer holds at most max_qubits gates,
+      // so that many operations imply depth >= 2*max_depth: the depth test alone decides
+      const bool trunc = ok && depth >= b.max_depth;
       const bool done = ok && (term || trunc);
       const bool want_metric = done || ((pk >> 22) & 1);
 
