@@ -80,3 +80,22 @@ def test_native_arm_json_line_on_gpu(cuda_device):
   assert rp["envs_total"] == 262144 and rp["value"] > 1e8
   assert cf["sp-bell-single-env"]["value"] > cf["sp-bell-single-env"]["cpu_baseline"]["value"]
   assert d["clocks"]["sm_max_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_bench_cost_models():
+  """The two analytic models bench.py reports beside the measured numbers: algorithmic FP64 flops of a tape (SURVEY 8d:
+  RX 6S, P 3S, CP 1.5S, CX 0, 8S per metric evaluation) and the 32-byte-sector model of the bytes a step really moves."""
+  import numpy as np
+  sys.path.insert(0, ROOT)
+  import bench
+  S = 64
+  #           P(q0)            RX(q1)           CP(c=0,w=2)      CX(c=1,w=0)      Terminate
+  tape = np.array([[[0.2, 0.5, 0.9, 1.0]], [[1.1, 1.2, 1.7, 1.0]], [[0.3, 2.1, 0.4, 1.0]], [[1.9, 0.2, 1.5, 1.0]],
+                   [[2.5, 0.0, 0.0, 0.0]]], dtype=np.float32)
+  flops = bench.tape_flops_per_env_step(tape, 3, S, metric_evals_per_env_step=0.2)
+  assert abs(flops - ((3 + 6 + 1.5 + 0 + 0) * S / 5 + 8 * S * 0.2)) < 1e-9
+  # SP, eta=3, S=8: state read 128 + obs 64 + 150 scalars + state writes: P on bit 0 -> all sectors (128), RX all
+  # (128), CP with bit 0 involved -> half (64), CX with control bit 1 -> half (64), Terminate + reset -> all (128)
+  got = bench.modelled_dram_bytes_per_env_step(tape, 3, 8, False, 64)
+  assert abs(got - (128 + 64 + 150 + (128 + 128 + 64 + 64 + 128) / 5)) < 1e-9
+  assert got < 32 * 8 + 8 * 8 + 96 + 150          # below the algorithmic figure + scalars: stores are skipped
