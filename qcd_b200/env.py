@@ -16,7 +16,7 @@ import numpy as np
 
 from .gym_compat import Box, Env, np_random
 from .targets import make_target
-from .vector_env import GATES, action_space_for
+from .vector_env import action_space_for
 
 
 class CircuitDesigner(Env):
@@ -38,7 +38,6 @@ class CircuitDesigner(Env):
     self.objective = objective
     self.target = make_target(objective, max_qubits, seed)                        # env.py:40
     import torch
-    from . import _lib
     from .batch import EnvBatch
     self._batch = b = EnvBatch(1, max_qubits, max_depth, objective, self.target, punish=punish, sparse=sparse,
                                autoreset=False, device=device, host_outputs=True, fused_stats=False)
