@@ -95,14 +95,22 @@ class CircuitDesigner(Env):
 
   # ------------------------------------------------------------------------------------------
   def render(self):
-    """Text drawing of the circuit built so far (the reference delegates to qiskit's drawer,
-    env.py:139-141; 'image' needs matplotlib+qiskit and is not available here)."""
+    """Drawing of the circuit built so far.  The reference delegates to qiskit's drawer (`qc.draw(mode)`,
+    env.py:139-141: 'text' -> an ASCII drawing, 'image' -> a matplotlib figure); qiskit is not available here, so
+    'text' is drawn by `_draw_text` and 'image' is an RGB array (H, W, 3) uint8 drawn with PIL (`_draw_image`)."""
     if self.render_mode is None: return None
-    if self.render_mode != 'text':
-      raise NotImplementedError("render_mode='image' needs qiskit's matplotlib drawer")
+    if self.render_mode == 'text': return self._draw_text()
+    if self.render_mode == 'image': return self._draw_image()
+    raise NotImplementedError(f"render_mode={self.render_mode!r}")
+
+  @staticmethod
+  def _label(kind, theta):
+    return {'p': 'P', 'rx': 'Rx', 'cp': 'P', 'cx': 'X'}[kind] + ('' if theta is None else f"({theta:.3g})")
+
+  def _draw_text(self) -> str:
     rows = [[f"q_{q}: "] for q in range(self.qubits)]
     for kind, qargs, theta in self._ops:
-      label = {'p': 'P', 'rx': 'Rx', 'cp': 'P', 'cx': 'X'}[kind] + ('' if theta is None else f"({theta:.3g})")
+      label = self._label(kind, theta)
       width = len(label) + 2
       tgt = qargs[-1]
       ctl = qargs[0] if len(qargs) == 2 else None
@@ -114,6 +122,28 @@ class CircuitDesigner(Env):
         else: cell = '─' * width
         rows[q].append(cell)
     return '\n'.join(''.join(r) for r in rows)
+
+  def _draw_image(self) -> np.ndarray:
+    """One column per gate, one horizontal wire per qubit; boxes on targets, dots on controls."""
+    from PIL import Image, ImageDraw
+    col, row, left, box = 64, 40, 48, (52, 24)
+    W, H = left + col * max(1, len(self._ops)) + 16, row * self.qubits + 16
+    img = Image.new('RGB', (W, H), 'white')
+    d = ImageDraw.Draw(img)
+    y = lambda q: 8 + row * q + row // 2
+    for q in range(self.qubits):
+      d.text((4, y(q) - 6), f"q{q}", fill='black')
+      d.line([(left - 16, y(q)), (W - 8, y(q))], fill='black', width=1)
+    for i, (kind, qargs, theta) in enumerate(self._ops):
+      x = left + col * i + col // 2
+      tgt = qargs[-1]
+      if len(qargs) == 2:
+        d.line([(x, y(qargs[0])), (x, y(tgt))], fill=(60, 60, 200), width=2)
+        d.ellipse([x - 4, y(qargs[0]) - 4, x + 4, y(qargs[0]) + 4], fill=(60, 60, 200))
+      d.rectangle([x - box[0] // 2, y(tgt) - box[1] // 2, x + box[0] // 2, y(tgt) + box[1] // 2],
+                  fill=(225, 235, 255), outline=(60, 60, 200))
+      d.text((x - box[0] // 2 + 3, y(tgt) - 6), self._label(kind, theta)[:9], fill='black')
+    return np.asarray(img, dtype=np.uint8)
 
   @property
   def state(self) -> np.ndarray:

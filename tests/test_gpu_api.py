@@ -92,6 +92,16 @@ def test_render_text(cuda_device):
   assert txt.count('\n') == 1 and 'Rx(1.57)' in txt and '■' in txt and 'X' in txt
 
 
+def test_render_image_is_an_rgb_array(cuda_device):
+  kw, seq = KATS['bell']
+  env = _make(**kw, render_mode='image'); env.reset()
+  empty = env.render()
+  for a in seq[:4]: env.step(a)
+  img = env.render()
+  assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3 and img.shape[0] == 2 * 40 + 16
+  assert img.shape[1] > empty.shape[1] and (img != 255).any()          # four gate columns were drawn
+
+
 def test_vector_env_host_path_and_semantics(cuda_device):
   from qcd_b200 import CircuitDesignerVectorEnv
   from oracle.batch_oracle import OracleBatch
