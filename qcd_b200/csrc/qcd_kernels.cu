@@ -765,6 +765,7 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
 #pragma unroll
     for (int k = 0; k < QCD_STATS_LEN; ++k) s_seq[4 + k] = 0.0;
   }
+  __syncthreads();                                            // s_nbad is zero before the decode below counts into it
 
   for (int t0 = 0; t0 < T; t0 += CH) {
     // ---- decode-ahead: step t0 + tid (env.py:90-100, the part that depends on the action alone)

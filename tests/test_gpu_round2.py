@@ -355,3 +355,30 @@ def test_step_outputs_do_not_depend_on_the_terminal_observation_buffer(cuda_devi
       assert torch.equal(getattr(fast, k), getattr(gen, k)), (t, k)
   _check(fast, ora, what="full tiles")
   assert torch.equal(fast.stats, gen.stats)
+
+
+@pytest.mark.parametrize("objective,eta,delta", [('SP-random', 9, 27), ('UC-random', 5, 20), ('SP-ghz5', 5, 20)])
+def test_replay_counts_invalid_actions_like_steps(cuda_device, objective, eta, delta):
+  """Tapes with out-of-range wires / gates: status, untouched state and the steps / bad_actions statistics of a replay
+  equal those of repeated steps and of the oracle."""
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(41)
+  N, T = 9, 40
+  target = make_target(objective, eta, seed=1)
+  tape_np = uniform_box_tape(rng, eta, T, N)
+  bad = rng.random((T, N)) < 0.3
+  tape_np[..., 1] = np.where(bad, eta + 0.5, tape_np[..., 1])          # wire out of range(eta)
+  tape_np[3, :, 0] = 3.2                                               # unknown gate
+  tape = torch.as_tensor(tape_np, device=cuda_device)
+  a = EnvBatch(N, eta, delta, objective, target); b = EnvBatch(N, eta, delta, objective, target)
+  ora = OracleBatch(N, eta, delta, objective, target)
+  rec = {'status': torch.zeros((T, N), dtype=torch.int8, device=cuda_device)}
+  b.replay(tape, rec)
+  for t in range(T):
+    a.step(tape[t]); ora.step(tape_np[t])
+    np.testing.assert_array_equal(rec['status'][t].cpu().numpy(), ora.status)
+  assert torch.equal(a.state, b.state) and torch.equal(a.meta, b.meta)
+  sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
+  assert sb[11] == sa[11] == ora.stats[11] > 0 and sb[10] == sa[10] == ora.stats[10]
+  np.testing.assert_allclose(sb, sa, rtol=1e-12, atol=1e-9)
+  _check(b, ora, what="replay with invalid actions")
