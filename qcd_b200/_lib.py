@@ -67,6 +67,10 @@ def load_library(path: str | None = None) -> C.CDLL:
   global _lib
   if _lib is not None and path is None:
     return _lib
+  # QCD_B200_LIB: a library built elsewhere from the same header (tuning variants of scripts/variants.sh); it is
+  # loaded as is: the ABI check below still applies, the staleness check cannot
+  cache = path is None
+  path = path or os.environ.get("QCD_B200_LIB") or None
   p = path or LIB_PATH
   if path is None:
     from .build import build_library, is_stale
@@ -102,7 +106,7 @@ def load_library(path: str | None = None) -> C.CDLL:
   lib.qcd_step_host.argtypes = [C.POINTER(QcdBatch), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(QcdHostOut), C.c_void_p]
   if lib.qcd_abi_version() != ABI_VERSION:
     raise RuntimeError(f"libqcd_b200.so ABI {lib.qcd_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
-  if path is None:
+  if cache:
     _lib = lib
   return lib
 

@@ -621,14 +621,17 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
 //     eta=6) or one shuffle per amplitude (2 of 6); shared memory is not touched by a gate at all.  For SP
 //     the lane bits are index bits 0..4 (coalesced I/O), the register bits 5..8, and a gate on a warp bit
 //     (3 of 12 at eta=12) exchanges amplitudes through shared memory — diagonal gates never move data;
-//   * the gate of a step is dispatched ONCE per step to code specialised on (register bit, gate kind):
-//     no per-pair switch, no index arithmetic (the 16 register slots are compile-time);
+//   * the gate of a step is dispatched ONCE per step, through an opcode the decode-ahead resolved (ROP_*), to code
+//     specialised on (register bit, gate kind; both register bits of a register-register CP): no per-pair switch,
+//     no index arithmetic (the 16 register slots are compile-time);
 //   * the depth stack lives in the lanes (lane q = qubit q): two shuffles, one max and one REDUX.MAX per
 //     step and warp give every warp the depth / truncation / reset decision without a broadcast or barrier;
 //   * the action-only part of the decode (floor, kind, sincos) is done one step per thread ahead of time;
-//   * only steps that need the metric (episode end, last step; every step when dense or recorded) pay a
-//     block reduction + barrier; their finalize (atan, cost, records, statistics) rotates over the warps;
-//   * the target stays in L1/L2 (read only on metric steps), statistics are flushed once per launch.
+//   * only steps that need the metric (episode end, last step; every step when dense or recorded) evaluate it; they
+//     leave one partial sum per warp in shared memory and are finalized per chunk, one metric step per thread
+//     (reg_finalize_chunk: atan, cost, shaping, records, statistics); only a dense reward / a carried return needs
+//     the short sequential pass of thread 0;
+//   * UC: every thread parks its 16 target amplitudes in shared memory; statistics are flushed once per launch.
 // Bit-identical amplitudes to qcd_step (same mul_phase / rot_rx).
 template <int LOG2S, bool UC>
 struct RegMap {
@@ -671,41 +674,155 @@ struct RegMap {
 
 struct __align__(16) RegStep { double cr, sr; int pk; int aux; };
 // pk: [2:0] kind [4:3] status [5] term [9:6] w [13:10] c [17:14] target position [21:18] control position [22] metric
-// needed whatever happens;  aux: [15:0] the 16 register slots the CONTROL allows (all for P / RX, the slots with
-// the control's register bit set for CP / CX, 0 = the control is a thread bit: decided per thread) [27:16] wire mask
+// needed whatever happens [27:23] opcode of the gate (ROP_*: ONE dispatch per step);  aux: [15:0] the 16 register slots
+// the CONTROL allows (all for P / RX, the slots with the control's register bit set for CP / CX, 0 = the control is a
+// thread bit: decided per thread) [27:16] wire mask
+//
+// Opcodes, resolved by the decode-ahead (they depend on the action alone): the target's register bit J and the
+// gate kind are compile-time in every case, and a CP between two register bits knows its four slots.
+constexpr int ROP_NONE = 0;
+constexpr int ROP_P = 1;        // + J: P on register bit J; also CP whose control is a thread bit (thread-predicated)
+constexpr int ROP_RX = 5;       // + J
+constexpr int ROP_CX = 9;       // + J: CX with the target on register bit J (control: register or thread bit)
+constexpr int ROP_CP2 = 13;     // + pair index of (J < J'): CP between two register bits
+constexpr int ROP_DIAG_T = 19;  // P / CP whose qubits are all thread bits: all 16 slots or none
+constexpr int ROP_LANE = 20;    // RX / CX with the target on a lane bit: one shuffle per amplitude
+constexpr int ROP_WARP = 21;    // RX / CX with the target on a warp bit (SP): exchange through shared memory
+__host__ __device__ constexpr int cp2_index(const int j, const int j2) {   // j < j2 < 4 -> 0..5
+  return j == 0 ? j2 - 1 : (j == 1 ? j2 + 1 : 5);
+}
 
 // slots k (of 16) whose bit j is set: 0xAAAA, 0xCCCC, 0xF0F0, 0xFF00
 __device__ __forceinline__ unsigned local_mask(const int j) { return (unsigned)(0xFF00F0F0CCCCAAAAull >> (16 * j)) & 0xffffu; }
 
 template <int J>
-__device__ __forceinline__ void reg_gate_local(const int kind, const unsigned cmask, const double cr, const double sr,
-                                               double2 (&a)[16]) {
+__device__ __forceinline__ void reg_gate_p(const double cr, const double sr, double2 (&a)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) if (k & (1 << J)) a[k] = mul_phase(a[k], cr, sr);
+}
+template <int J, int J2>
+__device__ __forceinline__ void reg_gate_cp2(const double cr, const double sr, double2 (&a)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) if ((k & (1 << J)) && (k & (1 << J2))) a[k] = mul_phase(a[k], cr, sr);
+}
+template <int J>
+__device__ __forceinline__ void reg_gate_rx(const double cr, const double sr, double2 (&a)[16]) {
   constexpr int B = 1 << J;
-  switch (kind) {
-    case K_P:
 #pragma unroll
-      for (int k = 0; k < 16; ++k) if (k & B) a[k] = mul_phase(a[k], cr, sr);
-      break;
-    case K_CP:
+  for (int k = 0; k < 16; ++k) if (!(k & B)) {
+    const double2 n0 = rot_rx(a[k], a[k | B], cr, sr), n1 = rot_rx(a[k | B], a[k], cr, sr);
+    a[k] = n0; a[k | B] = n1;
+  }
+}
+// swap the pair where the control bit is set (same for both members: c != w)
+template <int J>
+__device__ __forceinline__ void reg_gate_cx(const unsigned cmask, double2 (&a)[16]) {
+  constexpr int B = 1 << J;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) if ((k & B) && ((cmask >> k) & 1u)) a[k] = mul_phase(a[k], cr, sr);
-      break;
-    case K_RX:
+  for (int k = 0; k < 16; ++k) if (!(k & B)) {
+    const bool sw = (cmask >> k) & 1u;
+    const double2 lo = a[k], hi = a[k | B];
+    a[k].x = sw ? hi.x : lo.x; a[k].y = sw ? hi.y : lo.y;
+    a[k | B].x = sw ? lo.x : hi.x; a[k | B].y = sw ? lo.y : hi.y;
+  }
+}
+
+// Phase 2 of replay_reg_kernel: every metric step of a chunk is finalized here, by ALL threads of the CTA, once per
+// chunk.  Written to hold few values at a time: it is compiled between the 64 state registers every thread keeps
+// through the step loop and the 128-register budget, and anything wider makes the LOOP spill.
+template <bool UC, int NT, int NW>
+__device__ __forceinline__ void reg_finalize_chunk(const qcd_batch_t& b, const qcd_tape_out_t& out,
+                                                   const double2 (*s_msum)[NW], const int4* s_minfo, double2* s_mres,
+                                                   double2 (*s_fin)[2], double* s_seq, int* s_istat, const int nm,
+                                                   const int t0, const int T, const long env) {
+  const int tid = threadIdx.x;
+  const long N = b.n_envs;
+  const bool autoreset = b.flags & QCD_F_AUTORESET;
+
+  // ================= phase 2a: raw metric (sqrt / atan) and raw cost of every metric step, one step per thread
+  const double carried = s_seq[0];                             // (read before thread 0 may rewrite it in phase 2b)
+  for (int i = tid; i < nm; i += NT) {
+    double xa = 0.0, xb = 0.0;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) if (!(k & B)) {
-        const double2 n0 = rot_rx(a[k], a[k | B], cr, sr), n1 = rot_rx(a[k | B], a[k], cr, sr);
-        a[k] = n0; a[k | B] = n1;
+    for (int wv = 0; wv < NW; ++wv) { xa += s_msum[i][wv].x; xb += s_msum[i][wv].y; }
+    const int info = s_minfo[i].y;
+    s_mres[i] = make_double2(metric_from_sums<UC>(xa, xb), depth_cost(b, info & 0xff));
+    if (((info >> 16) & 3) == QCD_ST_OK && ((info >> 18) & 3)) atomicMax(&s_istat[7], i);   // last finished episode
+  }
+  __syncthreads();
+  // ================= phase 2b: what depends on the EARLIER steps of the episode (env.py:102-104: deltas of a dense
+  // reward; Monitor's running return), thread 0, results into s_fin.  A sparse reward is zero until the episode
+  // ends (env.py:134), so with auto-reset and no return carried in every metric step stands alone: skipped.
+  const bool standalone = (b.flags & QCD_F_SPARSE) && autoreset && carried == 0.0;
+  if (!standalone) {
+    if (tid == 0) {
+      EnvCtl e;
+      e.meta = make_uint4(0, 0, 0, 0);
+      e.ep_ret = s_seq[0]; e.last_m = s_seq[1]; e.last_c = s_seq[2];
+      for (int i = 0; i < nm; ++i) {
+        const int info = s_minfo[i].y;
+        e.status = (info >> 16) & 3; e.term = (info >> 18) & 1; e.trunc = (info >> 19) & 1;
+        e.ep_len = 0; e.cost_raw = s_mres[i].y;
+        const StepOut o = shape_step(b, e, s_mres[i].x);
+        s_fin[i][0] = make_double2(o.reward, o.metric);
+        s_fin[i][1] = make_double2(o.cost, e.ep_ret);
+        if (e.status == QCD_ST_OK && (e.term || e.trunc) && autoreset) { e.ep_ret = 0.0; e.last_m = 0.0; e.last_c = 0.0; }
       }
-      break;
-    default:   // K_CX: swap the pair where the control bit is set (same for both members: c != w)
-#pragma unroll
-      for (int k = 0; k < 16; ++k) if (!(k & B)) {
-        const bool sw = (cmask >> k) & 1u;
-        const double2 lo = a[k], hi = a[k | B];
-        a[k].x = sw ? hi.x : lo.x; a[k].y = sw ? hi.y : lo.y;
-        a[k | B].x = sw ? lo.x : hi.x; a[k | B].y = sw ? lo.y : hi.y;
-      }
-      break;
+      s_seq[0] = e.ep_ret; s_seq[1] = e.last_m; s_seq[2] = e.last_c;
+    }
+    __syncthreads();
+  }
+  // ================= phase 2c: shaping of stand-alone steps (env.py:133-135), records, Monitor latch, one metric step
+  // per thread; a finished episode counts into the integer statistics and leaves (r, m, c) in its s_fin slot
+  for (int i = tid; i < nm; i += NT) {
+    const int4 mi = s_minfo[i];
+    const int t = t0 + mi.x, depth = mi.y & 0xff, used_cnt = (mi.y >> 8) & 0xff, status = (mi.y >> 16) & 3;
+    const bool term = (mi.y >> 18) & 1, trunc = (mi.y >> 19) & 1;
+    StepOut o;
+    double ep_ret;
+    if (standalone) {
+      EnvCtl e;
+      e.meta = make_uint4(0, 0, 0, 0); e.ep_ret = 0.0; e.last_m = 0.0; e.last_c = 0.0; e.ep_len = 0;
+      e.status = status; e.term = term; e.trunc = trunc; e.cost_raw = s_mres[i].y;
+      o = shape_step(b, e, s_mres[i].x);
+      ep_ret = e.ep_ret;
+    } else {
+      const double2 f0 = s_fin[i][0], f1 = s_fin[i][1];
+      o.reward = f0.x; o.metric = f0.y; o.cost = f1.x; ep_ret = f1.y;
+    }
+    const long at = (long)t * N + env;
+    if (out.reward) out.reward[at] = o.reward;
+    if (out.metric) out.metric[at] = o.metric;
+    if (out.cost) out.cost[at] = o.cost;
+    if (out.depth) out.depth[at] = depth;
+    if (out.terminated) out.terminated[at] = term;
+    if (out.truncated) out.truncated[at] = trunc;
+    if (out.status) out.status[at] = (int8_t)status;
+    if (out.operations) out.operations[at] = mi.z;
+    if (out.used_wires) out.used_wires[at] = used_cnt;
+    if (t == T - 1) {
+      b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
+      b.depth[env] = depth; b.operations[env] = mi.z; b.used_wires[env] = used_cnt;
+      b.terminated[env] = term; b.truncated[env] = trunc; b.status[env] = (int8_t)status;
+    }
+    const bool done = status == QCD_ST_OK && (term || trunc);
+    if (done) {
+      const int ep_l = mi.w + 1;                               // (recorded before this step was counted, monitor.py:38)
+      // Monitor 'r' / 'l' of the env: the chunk's LAST finished episode stays (later chunks overwrite)
+      if (b.episode_return && i == s_istat[7]) { b.episode_return[env] = ep_ret; b.episode_length[env] = ep_l; }
+      atomicAdd(&s_istat[0], 1); atomicAdd(&s_istat[1], ep_l); atomicAdd(&s_istat[2], depth);
+      atomicAdd(&s_istat[3], mi.z); atomicAdd(&s_istat[4], used_cnt); atomicAdd(&s_istat[trunc ? 6 : 5], 1);
+    }
+    s_fin[i][0] = make_double2(done ? ep_ret : 0.0, done ? o.metric : 0.0);
+    s_fin[i][1] = make_double2(done ? o.cost : 0.0, 0.0);
+  }
+  __syncthreads();
+  // ================= phase 2d: the float64 statistics, summed in step order (three threads, one field each)
+  if (tid < 3) {
+    const double* f = reinterpret_cast<const double*>(&s_fin[0][0]) + tid;
+    double acc = s_seq[4 + (tid == 0 ? QCD_STAT_SUM_R : (tid == 1 ? QCD_STAT_SUM_M : QCD_STAT_SUM_C))];
+    for (int i = 0; i < nm; ++i) acc += f[4 * i];
+    s_seq[4 + (tid == 0 ? QCD_STAT_SUM_R : (tid == 1 ? QCD_STAT_SUM_M : QCD_STAT_SUM_C))] = acc;
   }
 }
 
@@ -720,10 +837,11 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   extern __shared__ __align__(16) double2 s_dynamic[];
   double2* const s_xchg = s_dynamic;                          // [S] exchange buffer (SP gates on warp bits)
   double2* const s_tgt = s_dynamic + M::XCHG_BYTES / sizeof(double2) + threadIdx.x;   // [16][NT] this thread's target slots
-  __shared__ RegStep s_tab[CH];                               // decoded steps of the chunk
+  __shared__ RegStep s_tab[CH + 1];                           // decoded steps of the chunk (+1: the loop fetches one ahead)
   __shared__ double2 s_msum[CH][NW];                          // per-warp metric sums of the chunk's metric steps
   __shared__ int4 s_minfo[CH];                                // their bookkeeping: {t, depth|used<<8|flags<<16, ops, ep_len}
   __shared__ double2 s_mres[CH];                              // their (raw metric, raw cost)
+  __shared__ double2 s_fin[CH][2];                            // their (reward, metric), (cost, ep_return) when sequential
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long env = blockIdx.x;
@@ -747,16 +865,19 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   }
   unsigned rmask = 0;                                         // slots that hold 1 after a reset (e0 / I)
 #pragma unroll
-  for (int k = 0; k < A; ++k) rmask |= (reset_amp(UC, b.n_qubits, tbase + M::koff(k)).x != 0.0 ? 1u : 0u) << k;
+  for (int k = 0; k < A; ++k) rmask |= (reset_amp(UC, M::ETA, tbase + M::koff(k)).x != 0.0 ? 1u : 0u) << k;
 
   // bookkeeping, replicated per WARP: lane q holds the depth of qubit q (QuantumCircuit.depth stack)
   int d = lane < 12 ? (int)reinterpret_cast<const uint8_t*>(b.meta)[env * 16 + lane] : 0;
   const uint32_t mw = reinterpret_cast<const uint32_t*>(b.meta)[env * 4 + 3];
   uint32_t ops = mw & 0xffffu, used = mw >> 16;
   int ep_len = b.ep_return ? b.ep_length[env] : 0;
-  // sequential episode state + statistics: shared memory, touched by thread 0 only (phase 2b)
+  // sequential episode state (thread 0, phase 2b) + statistics of the launch (phase 2c): shared memory
   __shared__ double s_seq[4 + QCD_STATS_LEN];                 // ep_return, last_metric, last_cost, -, statistics
   __shared__ int s_nbad;                                      // steps with an invalid action (counted by the decode)
+  // integer statistics of the launch {episodes, sum_l, sum_d, sum_o, sum_q, n_done, n_depth}; [7]: metric-step index
+  // of the current chunk's last finished episode
+  __shared__ int s_istat[8];
   if (tid == 0) {
     s_nbad = 0;
     s_seq[0] = b.ep_return ? b.ep_return[env] : 0.0;
@@ -764,6 +885,8 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
     s_seq[1] = l2.x; s_seq[2] = l2.y;
 #pragma unroll
     for (int k = 0; k < QCD_STATS_LEN; ++k) s_seq[4 + k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_istat[k] = 0;
   }
   __syncthreads();                                            // s_nbad is zero before the decode below counts into it
 
@@ -781,9 +904,22 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       if (k.kind == K_CP && tpos >= 4 && cpos < 4) { const int x = tpos; tpos = cpos; cpos = x; }
       const bool controlled = k.kind == K_CP || k.kind == K_CX;
       r.aux = (int)(!controlled ? 0xffffu : (cpos < 4 ? local_mask(cpos) : 0u)) | (((1 << k.w) | (1 << k.c)) << 16);
+      // the ONE dispatch of the step loop: target register bit and gate kind (and a register-register CP's slot
+      // set) become compile-time in the case bodies
+      int op = ROP_NONE;
+      if (k.kind != K_NONE) {
+        if (tpos < 4) {
+          op = k.kind == K_RX ? ROP_RX + tpos : (k.kind == K_CX ? ROP_CX + tpos : ROP_P + tpos);
+          if (k.kind == K_CP && cpos < 4) op = ROP_CP2 + (tpos < cpos ? cp2_index(tpos, cpos) : cp2_index(cpos, tpos));
+        } else if (k.kind == K_P || k.kind == K_CP) {
+          op = ROP_DIAG_T;
+        } else {
+          op = tpos < 9 ? ROP_LANE : ROP_WARP;
+        }
+      }
       // bit 22: the metric of this step is needed whatever happens (recorded / dense reward / last step)
       r.pk = k.kind | (k.status << 3) | ((k.term ? 1 : 0) << 5) | (k.w << 6) | (k.c << 10) | (tpos << 14) | (cpos << 18) |
-             ((metric_every_step || t0 + i == T - 1) ? (1 << 22) : 0);
+             ((metric_every_step || t0 + i == T - 1) ? (1 << 22) : 0) | (op << 23);
       s_tab[i] = r;
       if (k.status != QCD_ST_OK) atomicAdd(&s_nbad, 1);
     }
@@ -797,8 +933,9 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       const double cr = s_tab[si].cr, sr = s_tab[si].sr;
       const int aux = s_tab[si].aux;
       const int pk = n_pk;
+      n_pk = s_tab[si + 1].pk;                                 // (past the chunk's last step: never used; the whole
+                                                               // record fetched ahead makes the loop spill: measured -14 %)
       const int kind = pk & 7;
-      n_pk = s_tab[si + 1 < nsteps ? si + 1 : si].pk;
       // ---- QuantumCircuit.depth / count_ops / idle_wires (env.py:74,77,86): issued BEFORE the gate (independent of
       // it), so that the shuffle / REDUX latency hides behind the gate's arithmetic; consumed after it
       if (kind != K_NONE) {
@@ -811,46 +948,58 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       }
       const int depth = __reduce_max_sync(FULL, d);
 
-      if (kind != K_NONE) {
+      {
         const int tpos = (pk >> 14) & 15, cpos = (pk >> 18) & 15;
         // slots (of 16) this gate touches as far as the CONTROL is concerned (decoded ahead; 0 = thread-bit control)
         unsigned cmask = (unsigned)aux & 0xffffu;
         if (cmask == 0u) cmask = ((tpat >> cpos) & 1u) ? 0xffffu : 0u;
-        if (tpos < 4) {
-          switch (tpos) {
-            case 0: reg_gate_local<0>(kind, cmask, cr, sr, a); break;
-            case 1: reg_gate_local<1>(kind, cmask, cr, sr, a); break;
-            case 2: reg_gate_local<2>(kind, cmask, cr, sr, a); break;
-            default: reg_gate_local<3>(kind, cmask, cr, sr, a); break;
-          }
-        } else if (kind == K_P || kind == K_CP) {
-          // diagonal, target (and for CP also the control) held by the thread index: all 16 slots or none
-          if (((tpat >> tpos) & 1u) && cmask) {
+        switch ((pk >> 23) & 31) {
+#define QCD_ROP_J(J)                                                                        \
+          case ROP_P + J: if (cmask) reg_gate_p<J>(cr, sr, a); break;                          \
+          case ROP_RX + J: reg_gate_rx<J>(cr, sr, a); break;                                   \
+          case ROP_CX + J: reg_gate_cx<J>(cmask, a); break;
+          QCD_ROP_J(0) QCD_ROP_J(1) QCD_ROP_J(2) QCD_ROP_J(3)
+#undef QCD_ROP_J
+          case ROP_CP2 + cp2_index(0, 1): reg_gate_cp2<0, 1>(cr, sr, a); break;
+          case ROP_CP2 + cp2_index(0, 2): reg_gate_cp2<0, 2>(cr, sr, a); break;
+          case ROP_CP2 + cp2_index(0, 3): reg_gate_cp2<0, 3>(cr, sr, a); break;
+          case ROP_CP2 + cp2_index(1, 2): reg_gate_cp2<1, 2>(cr, sr, a); break;
+          case ROP_CP2 + cp2_index(1, 3): reg_gate_cp2<1, 3>(cr, sr, a); break;
+          case ROP_CP2 + cp2_index(2, 3): reg_gate_cp2<2, 3>(cr, sr, a); break;
+          case ROP_DIAG_T:
+            // diagonal, target (and for CP also the control) held by the thread index: all 16 slots or none
+            if (((tpat >> tpos) & 1u) && cmask) {
 #pragma unroll
-            for (int k = 0; k < A; ++k) a[k] = mul_phase(a[k], cr, sr);
-          }
-        } else if (tpos < 9) {                                 // partner = lane ^ xm: one shuffle per amplitude
-          const int xm = 1 << (tpos - 4);
+              for (int k = 0; k < A; ++k) a[k] = mul_phase(a[k], cr, sr);
+            }
+            break;
+          case ROP_LANE: {                                     // partner = lane ^ xm: one shuffle per amplitude
+            const int xm = 1 << (tpos - 4);
 #pragma unroll
-          for (int k = 0; k < A; ++k) {
-            double2 p;
-            p.x = __shfl_xor_sync(FULL, a[k].x, xm);
-            p.y = __shfl_xor_sync(FULL, a[k].y, xm);
-            if (kind == K_RX) a[k] = rot_rx(a[k], p, cr, sr);
-            else if ((cmask >> k) & 1u) a[k] = p;              // CX
-          }
-        } else if (M::WARP_TARGETS) {                          // partner in another warp: through shared memory
-          const int ptid = tid ^ (1 << (tpos - 4));
+            for (int k = 0; k < A; ++k) {
+              double2 p;
+              p.x = __shfl_xor_sync(FULL, a[k].x, xm);
+              p.y = __shfl_xor_sync(FULL, a[k].y, xm);
+              if (kind == K_RX) a[k] = rot_rx(a[k], p, cr, sr);
+              else if ((cmask >> k) & 1u) a[k] = p;            // CX
+            }
+          } break;
+          case ROP_WARP:
+            if (M::WARP_TARGETS) {                             // partner in another warp: through shared memory
+              const int ptid = tid ^ (1 << (tpos - 4));
 #pragma unroll
-          for (int k = 0; k < A; ++k) s_xchg[k * NT + tid] = a[k];
-          __syncthreads();
+              for (int k = 0; k < A; ++k) s_xchg[k * NT + tid] = a[k];
+              __syncthreads();
 #pragma unroll
-          for (int k = 0; k < A; ++k) {
-            const double2 p = s_xchg[k * NT + ptid];
-            if (kind == K_RX) a[k] = rot_rx(a[k], p, cr, sr);
-            else if ((cmask >> k) & 1u) a[k] = p;
-          }
-          __syncthreads();                                     // buffer free for the next exchange
+              for (int k = 0; k < A; ++k) {
+                const double2 p = s_xchg[k * NT + ptid];
+                if (kind == K_RX) a[k] = rot_rx(a[k], p, cr, sr);
+                else if ((cmask >> k) & 1u) a[k] = p;
+              }
+              __syncthreads();                                 // buffer free for the next exchange
+            }
+            break;
+          default: break;                                      // ROP_NONE: Terminate / invalid action
         }
       }
 
@@ -905,67 +1054,25 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
 #pragma unroll
           for (int k = 0; k < A; ++k) { fo[M::koff(k)] = (float)a[k].x; fo[S + M::koff(k)] = (float)a[k].y; }
         }
+        // (the mask is made opaque here: otherwise the compiler keeps the 16 high words of the reset values in
+        // registers through the whole loop, which the 128-register budget pays with spills)
+        unsigned rm = rmask;
+        asm volatile("" : "+r"(rm));
 #pragma unroll
-        for (int k = 0; k < A; ++k) a[k] = make_double2(((rmask >> k) & 1u) ? 1.0 : 0.0, 0.0);
+        for (int k = 0; k < A; ++k) a[k] = make_double2(__hiloint2double(((rm >> k) & 1u) ? 0x3ff00000 : 0, 0), 0.0);
         // keeps this a real branch: if-converted into 64 selects per step, the compiler carried two copies of
         // the state through the loop (128 MOVs + spills per step)
         asm volatile("" ::: "memory");
         d = 0; ops = 0; used = 0; ep_len = 0;
       }
     }
+    if (tid == 0) s_istat[7] = -1;
     __syncthreads();                                           // every warp's sums of the chunk are in shared memory
-
-    // ================= phase 2a: raw metric (sqrt / atan) and raw cost of every metric step, one step per thread
-    for (int i = tid; i < nm; i += NT) {
-      double xa = 0.0, xb = 0.0;
-#pragma unroll
-      for (int wv = 0; wv < NW; ++wv) { xa += s_msum[i][wv].x; xb += s_msum[i][wv].y; }
-      s_mres[i] = make_double2(metric_from_sums<UC>(xa, xb), depth_cost(b, s_minfo[i].y & 0xff));
-    }
-    __syncthreads();
-    // ================= phase 2b: the sequential part (env.py:102-104,133-135, Monitor, records), thread 0
-    if (tid == 0) {
-      EnvCtl e;
-      e.meta = make_uint4(0, 0, 0, 0);
-      e.ep_ret = s_seq[0]; e.last_m = s_seq[1]; e.last_c = s_seq[2];
-      double* st = s_seq + 4;
-      for (int i = 0; i < nm; ++i) {
-        const int4 mi = s_minfo[i];
-        const int t = t0 + mi.x, depth = mi.y & 0xff, used_cnt = (mi.y >> 8) & 0xff, status = (mi.y >> 16) & 3;
-        const bool term = (mi.y >> 18) & 1, trunc = (mi.y >> 19) & 1;
-        e.depth = depth; e.ops = mi.z; e.used_cnt = used_cnt; e.status = status; e.term = term; e.trunc = trunc;
-        e.ep_len = mi.w; e.cost_raw = s_mres[i].y;
-        const StepOut o = shape_step(b, e, s_mres[i].x);
-        const long at = (long)t * N + env;
-        if (out.reward) out.reward[at] = o.reward;
-        if (out.metric) out.metric[at] = o.metric;
-        if (out.cost) out.cost[at] = o.cost;
-        if (out.depth) out.depth[at] = depth;
-        if (out.terminated) out.terminated[at] = term;
-        if (out.truncated) out.truncated[at] = trunc;
-        if (out.status) out.status[at] = (int8_t)status;
-        if (out.operations) out.operations[at] = mi.z;
-        if (out.used_wires) out.used_wires[at] = used_cnt;
-        if (t == T - 1) {
-          b.reward[env] = o.reward; b.metric[env] = o.metric; b.cost[env] = o.cost;
-          b.depth[env] = depth; b.operations[env] = mi.z; b.used_wires[env] = used_cnt;
-          b.terminated[env] = term; b.truncated[env] = trunc; b.status[env] = (int8_t)status;
-        }
-        if (status == QCD_ST_OK && (term || trunc)) {
-          if (b.episode_return) { b.episode_return[env] = e.ep_ret; b.episode_length[env] = e.ep_len; }
-          st[QCD_STAT_EPISODES] += 1.0;
-          if (b.ep_return) { st[QCD_STAT_SUM_R] += e.ep_ret; st[QCD_STAT_SUM_L] += (double)e.ep_len; }
-          st[QCD_STAT_SUM_D] += (double)depth; st[QCD_STAT_SUM_O] += (double)mi.z; st[QCD_STAT_SUM_Q] += (double)used_cnt;
-          st[QCD_STAT_SUM_M] += o.metric; st[QCD_STAT_SUM_C] += o.cost;
-          if (trunc) st[QCD_STAT_N_DEPTH] += 1.0; else st[QCD_STAT_N_DONE] += 1.0;
-          if (autoreset) { e.ep_ret = 0.0; e.last_m = 0.0; e.last_c = 0.0; }
-        }
-      }
-      s_seq[0] = e.ep_ret; s_seq[1] = e.last_m; s_seq[2] = e.last_c;
-    }
+    reg_finalize_chunk<UC, NT, NW>(b, out, s_msum, s_minfo, s_mres, s_fin, s_seq, s_istat, nm, t0, T, env);
     // (the next chunk's first barrier orders these reads of s_minfo / s_mres before their next writes)
   }
 
+  __syncthreads();                                             // phase 2 of the last chunk (statistics) is complete
   // ---- the state (and the observation of the last step) go back to HBM once.  The addresses are rebuilt from
   // a fresh read of the CTA index, so that no pointer has to stay in a register through the step loop.
   {
@@ -988,6 +1095,11 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       if (b.stats) {
         double* stats = stats_slice(b, env);
         s_seq[4 + QCD_STAT_STEPS] = (double)(T - s_nbad); s_seq[4 + QCD_STAT_BAD_ACTIONS] = (double)s_nbad;
+        s_seq[4 + QCD_STAT_EPISODES] = (double)s_istat[0]; s_seq[4 + QCD_STAT_SUM_L] = (double)s_istat[1];
+        s_seq[4 + QCD_STAT_SUM_D] = (double)s_istat[2]; s_seq[4 + QCD_STAT_SUM_O] = (double)s_istat[3];
+        s_seq[4 + QCD_STAT_SUM_Q] = (double)s_istat[4]; s_seq[4 + QCD_STAT_N_DONE] = (double)s_istat[5];
+        s_seq[4 + QCD_STAT_N_DEPTH] = (double)s_istat[6];
+        if (!b.ep_return) { s_seq[4 + QCD_STAT_SUM_R] = 0.0; s_seq[4 + QCD_STAT_SUM_L] = 0.0; }   // no Monitor accumulators
 #pragma unroll
         for (int k = 0; k < QCD_STATS_LEN; ++k) if (s_seq[4 + k] != 0.0) atomicAdd(stats + k, s_seq[4 + k]);
       }
