@@ -727,6 +727,23 @@ __device__ __forceinline__ void reg_gate_cx(const unsigned cmask, double2 (&a)[1
   }
 }
 
+// env.py:106-111 on a register-resident state: this warp's share of |<psi|target>|^2 / ||U - V||_F^2
+template <int LOG2S, bool UC>
+__device__ __forceinline__ double2 reg_warp_metric(const double2 (&a)[16], const double2* s_tgt, const double2* tgt) {
+  using M = RegMap<LOG2S, UC>;
+  double pa[4] = {0.0, 0.0, 0.0, 0.0}, pb[4] = {0.0, 0.0, 0.0, 0.0};   // four independent chains
+#pragma unroll
+  for (int k = 0; k < M::A; ++k)
+    metric_acc<UC>(a[k], M::TGT_SMEM ? s_tgt[k * M::NT] : __ldg(tgt + M::koff(k)), pa[k & 3], pb[k & 3]);
+  double ra = (pa[0] + pa[1]) + (pa[2] + pa[3]), rb = (pb[0] + pb[1]) + (pb[2] + pb[3]);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    ra += __shfl_xor_sync(0xffffffffu, ra, off);
+    if (!UC) rb += __shfl_xor_sync(0xffffffffu, rb, off);
+  }
+  return make_double2(ra, rb);
+}
+
 // Phase 2 of replay_reg_kernel: every metric step of a chunk is finalized here, by ALL threads of the CTA, once per
 // chunk.  Written to hold few values at a time: it is compiled between the 64 state registers every thread keeps
 // through the step loop and the 128-register budget, and anything wider makes the LOOP spill.
@@ -856,9 +873,6 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   const double2* tgt = reinterpret_cast<const double2*>(b.target) +
                        ((b.flags & QCD_F_TARGET_PER_ENV) ? env * S : 0) + tbase;
 
-  double2 a[A];
-#pragma unroll
-  for (int k = 0; k < A; ++k) a[k] = gstate[M::koff(k)];
   if (M::TGT_SMEM) {
 #pragma unroll
     for (int k = 0; k < A; ++k) s_tgt[k * NT] = __ldg(tgt + M::koff(k));
@@ -866,12 +880,27 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
   unsigned rmask = 0;                                         // slots that hold 1 after a reset (e0 / I)
 #pragma unroll
   for (int k = 0; k < A; ++k) rmask |= (reset_amp(UC, M::ETA, tbase + M::koff(k)).x != 0.0 ? 1u : 0u) << k;
+  double2 a[A];
+  // the metric sums of the RESET state, once per launch: with the reference's own action sampler a third of the
+  // episodes ends on its first step (Terminate), and those are evaluated on e0 / I
+  __shared__ double2 s_m0[NW];
+  {
+#pragma unroll
+    for (int k = 0; k < A; ++k) a[k] = make_double2(((rmask >> k) & 1u) ? 1.0 : 0.0, 0.0);
+    const double2 r0 = reg_warp_metric<LOG2S, UC>(a, s_tgt, tgt);
+    if (lane == 0) s_m0[warp] = r0;
+    __syncwarp();
+  }
+  bool fresh = false;                                         // the registers hold exactly the reset state
+#pragma unroll
+  for (int k = 0; k < A; ++k) a[k] = gstate[M::koff(k)];
 
   // bookkeeping, replicated per WARP: lane q holds the depth of qubit q (QuantumCircuit.depth stack)
   int d = lane < 12 ? (int)reinterpret_cast<const uint8_t*>(b.meta)[env * 16 + lane] : 0;
   const uint32_t mw = reinterpret_cast<const uint32_t*>(b.meta)[env * 4 + 3];
   uint32_t ops = mw & 0xffffu, used = mw >> 16;
   int ep_len = b.ep_return ? b.ep_length[env] : 0;
+  int depth = __reduce_max_sync(FULL, d);                     // circuit depth = max over the qubits' counters
   // sequential episode state (thread 0, phase 2b) + statistics of the launch (phase 2c): shared memory
   __shared__ double s_seq[4 + QCD_STATS_LEN];                 // ep_return, last_metric, last_cost, -, statistics
   __shared__ int s_nbad;                                      // steps with an invalid action (counted by the decode)
@@ -933,8 +962,8 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       const double cr = s_tab[si].cr, sr = s_tab[si].sr;
       const int aux = s_tab[si].aux;
       const int pk = n_pk;
-      n_pk = s_tab[si + 1].pk;                                 // (past the chunk's last step: never used; the whole
-                                                               // record fetched ahead makes the loop spill: measured -14 %)
+      n_pk = s_tab[si + 1].pk;                                 // (past the chunk's last step: never used; fetching the
+                                                               // whole record ahead measured 2 % slower)
       const int kind = pk & 7;
       // ---- QuantumCircuit.depth / count_ops / idle_wires (env.py:74,77,86): issued BEFORE the gate (independent of
       // it), so that the shuffle / REDUX latency hides behind the gate's arithmetic; consumed after it
@@ -943,10 +972,11 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         const int dw = __shfl_sync(FULL, d, w), dc = __shfl_sync(FULL, d, c);
         const int lvl = min(max(dw, dc) + 1, 255);             // saturate (only past truncation)
         if (lane == w || lane == c) d = lvl;
+        depth = max(depth, lvl);                               // the new level is the only counter that grew
+        fresh = false;
         ops = min(ops + 1u, 0xffffu);
         used |= (unsigned)aux >> 16;
       }
-      const int depth = __reduce_max_sync(FULL, d);
 
       {
         const int tpos = (pk >> 14) & 15, cpos = (pk >> 18) & 15;
@@ -1016,17 +1046,9 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       if (want_metric) {
         // ---- env.py:106-111: partial sums of |<psi|target>|^2 / ||U - V||_F^2, one value per warp; they are
         // combined, shaped and emitted in phase 2
-        double pa[4] = {0.0, 0.0, 0.0, 0.0}, pb[4] = {0.0, 0.0, 0.0, 0.0};   // four independent chains
-#pragma unroll
-        for (int k = 0; k < A; ++k)
-          metric_acc<UC>(a[k], M::TGT_SMEM ? s_tgt[k * NT] : __ldg(tgt + M::koff(k)), pa[k & 3], pb[k & 3]);
-        double ra = (pa[0] + pa[1]) + (pa[2] + pa[3]), rb = (pb[0] + pb[1]) + (pb[2] + pb[3]);
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          ra += __shfl_xor_sync(FULL, ra, off);
-          if (!UC) rb += __shfl_xor_sync(FULL, rb, off);
-        }
-        if (lane == 0) s_msum[nm][warp] = make_double2(ra, rb);
+        // (an episode that ends right after a reset is evaluated on e0 / I: that sum is known since the prologue)
+        const double2 r2 = fresh ? s_m0[warp] : reg_warp_metric<LOG2S, UC>(a, s_tgt, tgt);
+        if (lane == 0) s_msum[nm][warp] = r2;
         if (tid == 0)
           s_minfo[nm] = make_int4(si, depth | (__popc(used) << 8) | (status << 16) | ((int)term << 18) | ((int)trunc << 19),
                                   (int)ops, ep_len);
@@ -1056,14 +1078,18 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         }
         // (the mask is made opaque here: otherwise the compiler keeps the 16 high words of the reset values in
         // registers through the whole loop, which the 128-register budget pays with spills)
-        unsigned rm = rmask;
-        asm volatile("" : "+r"(rm));
+        if (!fresh) {                                          // (untouched since the last reset: nothing to rewrite)
+          unsigned rm = rmask;
+          asm volatile("" : "+r"(rm));
 #pragma unroll
-        for (int k = 0; k < A; ++k) a[k] = make_double2(__hiloint2double(((rm >> k) & 1u) ? 0x3ff00000 : 0, 0), 0.0);
-        // keeps this a real branch: if-converted into 64 selects per step, the compiler carried two copies of
-        // the state through the loop (128 MOVs + spills per step)
-        asm volatile("" ::: "memory");
-        d = 0; ops = 0; used = 0; ep_len = 0;
+          for (int k = 0; k < A; ++k)                          // high word of 1.0 where bit k is set (two instructions)
+            a[k] = make_double2(__hiloint2double((int)((rm & (1u << k)) * (0x3ff00000u >> k)), 0), 0.0);
+          // keeps this a real branch: if-converted into 64 selects per step, the compiler carried two copies of
+          // the state through the loop (128 MOVs + spills per step)
+          asm volatile("" ::: "memory");
+          fresh = true;
+        }
+        d = 0; depth = 0; ops = 0; used = 0; ep_len = 0;
       }
     }
     if (tid == 0) s_istat[7] = -1;
