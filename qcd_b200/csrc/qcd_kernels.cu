@@ -1042,6 +1042,9 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       const bool trunc = ok && depth >= b.max_depth;
       const bool done = ok && (term || trunc);
       const bool want_metric = done || ((pk >> 22) & 1);
+      // the step's bookkeeping record is written by lane 0 of ONE warp, rotating over the warps (every warp holds the
+      // same depth / ops / used / ep_len): warp 0 alone doing it reached the end of the chunk ~4 % after the others
+      const bool scribe = lane == 0 && warp == (si & (NW - 1));
 
       if (want_metric) {
         // ---- env.py:106-111: partial sums of |<psi|target>|^2 / ||U - V||_F^2, one value per warp; they are
@@ -1049,11 +1052,11 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         // (an episode that ends right after a reset is evaluated on e0 / I: that sum is known since the prologue)
         const double2 r2 = fresh ? s_m0[warp] : reg_warp_metric<LOG2S, UC>(a, s_tgt, tgt);
         if (lane == 0) s_msum[nm][warp] = r2;
-        if (tid == 0)
+        if (scribe)
           s_minfo[nm] = make_int4(si, depth | (__popc(used) << 8) | (status << 16) | ((int)term << 18) | ((int)trunc << 19),
                                   (int)ops, ep_len);
         ++nm;
-      } else if (tid == 0) {
+      } else if (scribe) {
         // ---- light step (sparse reward, episode goes on, nobody records the metric): reward and shaped cost
         // are 0 (env.py:134), the metric is not evaluated, ep_return is unchanged
         int tt = t0 + si;
