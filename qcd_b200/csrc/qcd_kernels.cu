@@ -688,6 +688,8 @@ constexpr int ROP_CP2 = 13;     // + pair index of (J < J'): CP between two regi
 constexpr int ROP_DIAG_T = 19;  // P / CP whose qubits are all thread bits: all 16 slots or none
 constexpr int ROP_LANE = 20;    // RX / CX with the target on a lane bit: one shuffle per amplitude
 constexpr int ROP_WARP = 21;    // RX / CX with the target on a warp bit (SP): exchange through shared memory
+constexpr int ROP_LANE_CX = 22; // + J': CX with the target on a lane bit and the control on register bit J': only
+                                // the eight slots with that bit set are exchanged
 __host__ __device__ constexpr int cp2_index(const int j, const int j2) {   // j < j2 < 4 -> 0..5
   return j == 0 ? j2 - 1 : (j == 1 ? j2 + 1 : 5);
 }
@@ -943,7 +945,7 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         } else if (k.kind == K_P || k.kind == K_CP) {
           op = ROP_DIAG_T;
         } else {
-          op = tpos < 9 ? ROP_LANE : ROP_WARP;
+          op = tpos < 9 ? ((k.kind == K_CX && cpos < 4) ? ROP_LANE_CX + cpos : ROP_LANE) : ROP_WARP;
         }
       }
       // bit 22: the metric of this step is needed whatever happens (recorded / dense reward / last step)
@@ -978,7 +980,7 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
         used |= (unsigned)aux >> 16;
       }
 
-      {
+      if (kind != K_NONE) {                                    // (Terminate / invalid action: no gate, no dispatch)
         const int tpos = (pk >> 14) & 15, cpos = (pk >> 18) & 15;
         // slots (of 16) this gate touches as far as the CONTROL is concerned (decoded ahead; 0 = thread-bit control)
         unsigned cmask = (unsigned)aux & 0xffffu;
@@ -1014,6 +1016,16 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
               else if ((cmask >> k) & 1u) a[k] = p;            // CX
             }
           } break;
+#define QCD_ROP_LANE_CX(J2)                                                                 \
+          case ROP_LANE_CX + J2: {                                                             \
+            const int xm = 1 << (tpos - 4);                                                    \
+            _Pragma("unroll") for (int k = 0; k < A; ++k) if (k & (1 << J2)) {                 \
+              a[k].x = __shfl_xor_sync(FULL, a[k].x, xm);                                      \
+              a[k].y = __shfl_xor_sync(FULL, a[k].y, xm);                                      \
+            }                                                                                  \
+          } break;
+          QCD_ROP_LANE_CX(0) QCD_ROP_LANE_CX(1) QCD_ROP_LANE_CX(2) QCD_ROP_LANE_CX(3)
+#undef QCD_ROP_LANE_CX
           case ROP_WARP:
             if (M::WARP_TARGETS) {                             // partner in another warp: through shared memory
               const int ptid = tid ^ (1 << (tpos - 4));
