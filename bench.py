@@ -407,8 +407,9 @@ def run_configs(args, torch, dist, dev, rank, world, stream):
                    "metric_evaluations_per_env_step": evals, "peak_source": fsrc,
                    "note": "state register-resident for the whole tape: HBM traffic is one state in/out per launch (3 % of "
                            "the copy peak); FP64 is the only roofline left.  ncu (profiles/r02_summary.md): FP64 pipe 19 % "
-                           "active, issue slots 51 % - the kernel is issue/latency-bound by its control flow (per-step decode, "
-                           "depth bookkeeping, reset), not by DFMA throughput"},
+                           "active, issue slots 51 %, shared-memory/shuffle pipe 49 % - bound by per-step latency, the gate "
+                           "dispatch and the shared-memory traffic of the metric (64 KiB of target per evaluation), not by "
+                           "DFMA throughput"},
       "cpu_baseline": cpu(objective, eta, delta, tape_np[:, :16], 3.0)}
   del br, tape
   torch.cuda.empty_cache()
