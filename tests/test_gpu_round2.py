@@ -5,6 +5,8 @@
 * BASELINE.json configs[3] and configs[4] at their FULL sizes against the oracle on a strided sample;
 * the terminal observation of `qcd_replay`, per-env targets through `step_host`.
 """
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -382,3 +384,43 @@ def test_replay_counts_invalid_actions_like_steps(cuda_device, objective, eta, d
   assert sb[11] == sa[11] == ora.stats[11] > 0 and sb[10] == sa[10] == ora.stats[10]
   np.testing.assert_allclose(sb, sa, rtol=1e-12, atol=1e-9)
   _check(b, ora, what="replay with invalid actions")
+
+
+@pytest.mark.parametrize("objective,eta,delta", [('UC-random', 5, 20), ('SP-random', 9, 27), ('UC-random', 6, 24)])
+@pytest.mark.parametrize("mode", ["no_autoreset", "carried_return", "dense_long"])
+def test_replay_finalize_paths_equal_repeated_steps(cuda_device, objective, eta, delta, mode):
+  """replay_reg_kernel finalizes the metric steps of a chunk one per thread; what depends on earlier steps of the
+  episode goes through a sequential pass first.  The cases the other replay tests do not reach: no auto-reset (the
+  return keeps accumulating after an episode ended), a sparse-reward batch that carries a non-zero return into the
+  launch, and a dense reward over a tape longer than one 128-step chunk.  Everything must equal T qcd_step calls."""
+  from qcd_b200.batch import EnvBatch
+  rng = np.random.default_rng(zlib.crc32(repr((objective, eta, mode)).encode()))
+  N, T = 7, (300 if mode == "dense_long" else 40)
+  kw = dict(punish=True, sparse=mode != "dense_long", autoreset=mode != "no_autoreset")
+  target = make_target(objective, eta, seed=5)
+  a = EnvBatch(N, eta, delta, objective, target, **kw)
+  b = EnvBatch(N, eta, delta, objective, target, **kw)
+  if mode == "carried_return":
+    for x in (a, b):
+      x.ep_return.fill_(0.375); x.ep_length.fill_(3)
+  tape = torch.as_tensor(uniform_box_tape(rng, eta, T, N), device=cuda_device)
+  rec = {k: torch.zeros((T, N), dtype=dt, device=cuda_device) for k, dt in
+         [('reward', torch.float64), ('metric', torch.float64), ('cost', torch.float64), ('depth', torch.int32),
+          ('terminated', torch.uint8), ('truncated', torch.uint8)]}
+  b.replay(tape, rec)
+  for t in range(T):
+    a.step(tape[t])
+    for k in rec:
+      x, y = rec[k][t], getattr(a, k)
+      if x.dtype.is_floating_point:
+        assert torch.allclose(x, y, atol=1e-13, rtol=0, equal_nan=True), (k, t)
+      else:
+        assert torch.equal(x, y), (k, t)
+  assert torch.equal(a.state, b.state) and torch.equal(a.meta, b.meta) and torch.equal(a.obs, b.obs)
+  assert torch.equal(a.ep_length, b.ep_length) and torch.equal(a.episode_length, b.episode_length)
+  assert torch.allclose(a.ep_return, b.ep_return, atol=1e-12, rtol=0)
+  assert torch.allclose(a.episode_return, b.episode_return, atol=1e-12, rtol=0)
+  assert torch.allclose(a.last, b.last, atol=1e-13, rtol=0)
+  sa, sb = a.fold_stats().cpu().numpy(), b.fold_stats().cpu().numpy()
+  np.testing.assert_allclose(sb, sa, rtol=1e-12, atol=1e-9)
+  assert sa[0] > 0                                     # episodes did finish
