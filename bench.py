@@ -772,9 +772,20 @@ def run_native(args):
     alg_bytes = N * (32 * S + (8 * S if obs_mode != 'none' else 0) + 96 + 16 * REPLAY_T)
   achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
   modelled = modelled_dram_bytes_per_env_step(tape_np, eta, S, 'UC' in objective, 8 * S if obs_mode != 'none' else 0)
-  traffic = None      # DRAM bytes cannot be measured outside the profiler; the ncu figures are in profiles/r02_summary.md
+  # DRAM bytes cannot be measured outside the profiler: `traffic` is the steady-state ncu figure of profiles/traffic.json
+  # (same workload, same env count, replicas rotating as here), else null
+  traffic, traffic_src = None, None
+  try:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+      rec = json.load(f).get(args.workload)
+    if mode == 'step' and rec and rec["envs"] == N and not args.no_rotate:
+      traffic = rec["bytes"]
+      traffic_src = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of %d launches in steady state "
+                     "(profiles/traffic.json, scripts/r3_traffic.sh)" % rec["launches"])
+  except (OSError, ValueError, KeyError):
+    pass
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-              "traffic": traffic, "peak_source": peak_src, "kernel": "qcd::%s<log2S=%d,%s>" % (
+              "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "qcd::%s<log2S=%d,%s>" % (
                   ("step_warp_kernel" if S <= 128 else "qcd_kernel(pair-streaming step)") if mode == 'step' else
                   ("replay_reg_kernel" if S >= 512 else "replay_warp_kernel"),
                   int(np.log2(S)), "UC" if 'UC' in objective else "SP"),
