@@ -101,7 +101,8 @@ def test_invalid_actions_status_and_masked_reset(cuda_device):
   _cmp(gpu, ora, what="masked reset")
 
 
-@pytest.mark.parametrize("objective,eta,delta", CONFIGS + [('SP-random', 12, 36), ('UC-random', 6, 24), ('SP-random', 11, 30)])
+@pytest.mark.parametrize("objective,eta,delta", CONFIGS + [('SP-random', 12, 36), ('UC-random', 6, 24), ('SP-random', 11, 30),
+                                                          ('SP-random', 10, 30), ('SP-random', 9, 27), ('UC-random', 5, 20)])
 @pytest.mark.parametrize("sparse", [True, False])
 def test_replay_equals_repeated_steps(cuda_device, objective, eta, delta, sparse):
   """qcd_replay(T) must leave every buffer exactly as T qcd_step launches do (same arithmetic,
