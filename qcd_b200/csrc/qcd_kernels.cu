@@ -622,10 +622,12 @@ qcd_kernel(const qcd_batch_t b, const void* __restrict__ actions, const int act_
 //     the lane bits are index bits 0..4 (coalesced I/O), the register bits 5..8, and a gate on a warp bit
 //     (3 of 12 at eta=12) exchanges amplitudes through shared memory — diagonal gates never move data;
 //   * the gate of a step is dispatched ONCE per step, through an opcode the decode-ahead resolved (ROP_*), to code
-//     specialised on (register bit, gate kind; both register bits of a register-register CP): no per-pair switch,
-//     no index arithmetic (the 16 register slots are compile-time);
-//   * the depth stack lives in the lanes (lane q = qubit q): two shuffles, one max and one REDUX.MAX per
-//     step and warp give every warp the depth / truncation / reset decision without a broadcast or barrier;
+//     specialised on (register bit, gate kind; both register bits of a register-register CP; the control's register
+//     bit of a CX on a lane bit): no per-pair switch, no index arithmetic (the 16 register slots are compile-time);
+//     steps without a gate skip the dispatch;
+//   * the depth stack lives in the lanes (lane q = qubit q): two shuffles and a max per gate, the circuit depth is the
+//     scalar recurrence max(depth, new level): every warp has the depth / truncation / reset decision without a
+//     broadcast or barrier;
 //   * the action-only part of the decode (floor, kind, sincos) is done one step per thread ahead of time;
 //   * only steps that need the metric (episode end, last step; every step when dense or recorded) evaluate it; they
 //     leave one partial sum per warp in shared memory and are finalized per chunk, one metric step per thread
