@@ -15,4 +15,3 @@ print('value %.4e frac %.3f modelled %.3f ms %.5f e2e %.4e ref %.4e e2e/ref %.0f
 print('graph_len', d['config']['graph_len'], 'gpu_launches', d['gpu_launches'], 'clocks', d['clocks'])
 for k,v in d['configs'].items(): print(k, '%.4e' % v['value'], (v.get('roofline') or {}).get('frac'), (v.get('cpu_baseline') or {}).get('value'))
 PY
-scripts/r3_profile_replay.sh r3f
