@@ -703,7 +703,8 @@ def run_native(args):
     # previous results have arrived on the host, so the RL data dependence holds per group while group g's
     # D2H overlaps group g+1's H2D and kernel.  G = 1 is the plain synchronous step_host.
     e2e_obs = 'none' if (obs_mode == 'none' or args.e2e_no_obs) else args.e2e_obs
-    venv = CircuitDesignerVectorEnv(N, eta, delta, objective, target=target, device=dev, obs_mode=e2e_obs)
+    venv = CircuitDesignerVectorEnv(N, eta, delta, objective, target=target, device=dev, obs_mode=e2e_obs,
+                                    zero_copy_scalars=not args.e2e_copy_scalars)
     venv.reset()
     Ke = max(3, min(K, args.e2e_steps))
     G = max(1, args.e2e_groups)
@@ -746,6 +747,9 @@ def run_native(args):
                    "streams (pinned host buffers, one event wait per group and step)" % (G, G)) if G > 1 else
                   "CircuitDesignerVectorEnv.step_host -> qcd_step_host (pinned host buffers, sync per step)",
            "groups": G, "obs_copied": e2e_obs != 'none',
+           "scalars": ("reward / terminated / truncated written by the step kernel straight into the pinned host arrays "
+                       "(zero_copy_scalars=True; the bytes still cross PCIe and are counted in d2h_bytes_per_step)")
+                      if not args.e2e_copy_scalars else "reward / terminated / truncated copied D2H",
            "obs_rows": {"state": "compact state half [N, 2S] float32, one contiguous D2H", "full": "reference rows "
                         "[N, 4S], pitched D2H of the state half", "none": "no observations"}[e2e_obs]}
     del venv
@@ -855,6 +859,9 @@ def main():
   ap.add_argument("--no-stats", action="store_true", help="do not accumulate episode statistics in the step kernel")
   ap.add_argument("--cpu-seconds", type=float, default=10.0)
   ap.add_argument("--e2e-steps", type=int, default=200)
+  ap.add_argument("--e2e-copy-scalars", action="store_true",
+                  help="e2e: D2H copies of reward / terminated / truncated instead of the kernel writing them into the "
+                       "pinned host arrays itself (zero_copy_scalars=False)")
   ap.add_argument("--e2e-no-obs", action="store_true", help="e2e without the observation D2H copy")
   ap.add_argument("--e2e-groups", type=int, default=2, help="env groups in flight on the host path (1 = synchronous)")
   ap.add_argument("--e2e-obs", default="state", choices=["state", "full"],

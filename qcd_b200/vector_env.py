@@ -41,8 +41,14 @@ class CircuitDesignerVectorEnv(VectorEnvBase):
   def __init__(self, num_envs: int, max_qubits: int, max_depth: int, objective: str,
                punish=True, sparse=True, seed=None, target=None, device=None,
                obs_mode: str = 'full', final_obs: bool = False, autoreset: bool = True,
-               raise_on_invalid: bool = False, episode_window: int = 0, render_mode=None):
+               raise_on_invalid: bool = False, episode_window: int = 0, render_mode=None,
+               zero_copy_scalars: bool = False):
     self.num_envs = int(num_envs)
+    # host path (step_host*): True = the step kernel writes the requested scalar results straight into the pinned host
+    # arrays (see _host_desc) and only the observation rows are copied; the DEVICE tensors of those scalars
+    # (batch.reward, .terminated, .truncated, ...) are then not outputs of such a step, so leave it off when device
+    # code (accumulate_stats, an episode window) consumes them after a host step
+    self.zero_copy_scalars = bool(zero_copy_scalars)
     self.qubits, self.depth = max_qubits, max_depth
     self.max_steps = max_depth * max_qubits * 2
     self.punish, self.sparse, self.objective = punish, sparse, objective
@@ -142,11 +148,26 @@ class CircuitDesignerVectorEnv(VectorEnvBase):
       self._groups = None
     return self._host
 
+  _SCALARS = ('reward', 'metric', 'cost', 'depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status')
+
+  def _host_desc(self, h, lo, hi, copy_info):
+    """`qcd_batch_t` of the env range [lo, hi) for the HOST path: the requested per-step scalar outputs point at
+    the rows [lo, hi) of the pinned host arrays (UVA maps them into the device address space), so the step kernel
+    writes them over PCIe itself and only the observation rows need the copy engine (one transfer instead of
+    four to ten per group and step).  The device-side tensors of those scalars are NOT written by such a step."""
+    key = ('desc', lo, hi, bool(copy_info))
+    if key not in h:
+      c = self.batch.sub_batch(lo, hi)
+      if self.zero_copy_scalars:
+        for k in (self._SCALARS if copy_info else ('reward', 'terminated', 'truncated')):
+          setattr(c, k, h[k].data_ptr() + lo * h[k].element_size())
+      h[key] = c
+    return h[key]
+
   def _host_out(self, h, lo, copy_obs, copy_info):
     """qcd_host_out_t whose destinations are the rows [lo, ...) of the pinned host arrays."""
     b = self.batch
-    names = ('reward', 'metric', 'cost', 'depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status') \
-        if copy_info else ('reward', 'terminated', 'truncated')
+    names = () if self.zero_copy_scalars else (self._SCALARS if copy_info else ('reward', 'terminated', 'truncated'))
     out = _lib.QcdHostOut(obs_stride=b.obs_stride)
     for k in names:
       setattr(out, k, h[k].data_ptr() + lo * h[k].element_size())
@@ -168,12 +189,14 @@ class CircuitDesignerVectorEnv(VectorEnvBase):
     dt = torch.float64 if a.dtype == np.float64 else torch.float32
     h = self._host_buffers(dt)
     h['np']['actions'][...] = a.reshape(self.num_envs, 4)
+    import ctypes as C
     b = self.batch
     out = self._host_out(h, 0, copy_obs, copy_info)
+    desc = self._host_desc(h, 0, self.num_envs, copy_info)
     stream = torch.cuda.current_stream(self.device)
     with torch.cuda.device(self.device):
       _lib.check(b.lib.qcd_step_host(
-          b._cref, h['actions'].data_ptr(), h['actions_dev'].data_ptr(),
+          C.byref(desc), h['actions'].data_ptr(), h['actions_dev'].data_ptr(),
           _lib.ACT_F64 if dt == torch.float64 else _lib.ACT_F32, out, stream.cuda_stream), "qcd_step_host")
     stream.synchronize()
     n = h['np']
@@ -196,7 +219,7 @@ class CircuitDesignerVectorEnv(VectorEnvBase):
       self._groups = []
       for g in range(groups):
         lo, hi = shard_range(self.num_envs, g, groups)
-        self._groups.append({'lo': lo, 'hi': hi, 'c': self.batch.sub_batch(lo, hi),
+        self._groups.append({'lo': lo, 'hi': hi,
                              'stream': torch.cuda.Stream(self.device), 'event': torch.cuda.Event(),
                              'pending': False, 'args': None})
     return [(g['lo'], g['hi']) for g in self._groups]
@@ -218,7 +241,8 @@ class CircuitDesignerVectorEnv(VectorEnvBase):
     esz = h['actions'].element_size() * 4
     with torch.cuda.device(self.device):
       _lib.check(self.batch.lib.qcd_step_host(
-          C.byref(g['c']), h['actions'].data_ptr() + lo * esz, h['actions_dev'].data_ptr() + lo * esz,
+          C.byref(self._host_desc(h, lo, hi, copy_info)), h['actions'].data_ptr() + lo * esz,
+          h['actions_dev'].data_ptr() + lo * esz,
           _lib.ACT_F64 if dt == torch.float64 else _lib.ACT_F32, out, g['stream'].cuda_stream), "qcd_step_host")
     g['event'].record(g['stream'])
     g['pending'], g['args'] = True, (copy_obs, copy_info)

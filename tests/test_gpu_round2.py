@@ -20,12 +20,14 @@ TOL = 1e-12
 OBS_TOL = 1.2e-7
 
 
-def _check(gpu, ora, sel=None, what=""):
+def _check(gpu, ora, sel=None, what="", skip=()):
   """ints bit-exact, floats <= 1e-12, float32 observations <= 1 ulp; `sel` = env indices of `gpu` that `ora` holds."""
   pick = (lambda t: t.cpu().numpy()) if sel is None else (lambda t: t[sel].cpu().numpy())
   for name in ('depth', 'operations', 'used_wires', 'terminated', 'truncated', 'status', 'meta', 'ep_length'):
+    if name in skip: continue
     np.testing.assert_array_equal(pick(getattr(gpu, name)), getattr(ora, name), err_msg=f"{what}:{name}")
   for name in ('reward', 'metric', 'cost', 'ep_return', 'state'):
+    if name in skip: continue
     np.testing.assert_allclose(pick(getattr(gpu, name)), getattr(ora, name), atol=TOL, rtol=0, err_msg=f"{what}:{name}")
   if gpu.obs is not None:
     np.testing.assert_allclose(pick(gpu.obs), ora.obs, atol=OBS_TOL, rtol=0, err_msg=f"{what}:obs")
@@ -202,14 +204,16 @@ def test_fold_stats_sums_and_clears_the_replicas(cuda_device):
   assert float(gpu._stats_raw.abs().sum()) == 0 and want[10].item() == 12 * N
 
 
-@pytest.mark.parametrize("groups", [2, 3])
-def test_pipelined_host_groups_match_oracle(cuda_device, groups):
+@pytest.mark.parametrize("groups,zero_copy", [(2, True), (3, True), (2, False)])
+def test_pipelined_host_groups_match_oracle(cuda_device, groups, zero_copy):
   """step_host_async / step_host_wait: env groups stepped on their own streams; every group's results are
-  those of the oracle, whatever the interleaving, and the compact observation rows are the state halves."""
+  those of the oracle, whatever the interleaving, and the compact observation rows are the state halves.
+  zero_copy: the kernel writes reward / terminated / truncated into the pinned host arrays itself (the device
+  tensors of those three are then not the step's outputs); otherwise they are copied like the observations."""
   from qcd_b200 import CircuitDesignerVectorEnv
   rng = np.random.default_rng(12)
   N, eta, delta, T = 1000, 5, 20, 30
-  venv = CircuitDesignerVectorEnv(N, eta, delta, 'SP-ghz5', obs_mode='state')
+  venv = CircuitDesignerVectorEnv(N, eta, delta, 'SP-ghz5', obs_mode='state', zero_copy_scalars=zero_copy)
   ora = OracleBatch(N, eta, delta, 'SP-ghz5', venv.target, obs_mode='state')
   venv.reset()
   ranges = venv.host_groups(groups)
@@ -235,7 +239,7 @@ def test_pipelined_host_groups_match_oracle(cuda_device, groups):
       np.testing.assert_allclose(r, ora.reward[lo:hi], atol=TOL, rtol=0)
       np.testing.assert_array_equal(term, ora.terminated[lo:hi].astype(bool))
       np.testing.assert_array_equal(trunc, ora.truncated[lo:hi].astype(bool))
-  _check(venv.batch, ora, what="groups end")
+  _check(venv.batch, ora, what="groups end", skip=('reward', 'terminated', 'truncated') if zero_copy else ())
   tobs = venv.target_obs
   assert tobs.shape == (64,) and tobs.dtype == np.float32
   assert venv.episode_stats()['steps'] == N * T
