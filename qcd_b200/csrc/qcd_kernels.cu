@@ -299,7 +299,11 @@ __device__ __forceinline__ double2 reset_amp(bool uc, int eta, int i) {
 // step, register-resident step, shared-memory replay) produces bit-identical amplitudes.
 // own * e^{i th}, e^{i th} = (cr, sr)
 __device__ __forceinline__ double2 mul_phase(const double2 a, const double cr, const double sr) {
-  return make_double2(__fma_rn(a.x, cr, -__dmul_rn(a.y, sr)), __fma_rn(a.x, sr, __dmul_rn(a.y, cr)));
+  // (.y first: it can take a.y's register once both products exist, then .x takes a.x's - no moves)
+  const double p = __dmul_rn(a.y, sr), q = __dmul_rn(a.y, cr);
+  const double ny = __fma_rn(a.x, sr, q);
+  const double nx = __fma_rn(a.x, cr, -p);
+  return make_double2(nx, ny);
 }
 // RX row: c*own - i*s*partner  (the same expression for both amplitudes of the pair)
 __device__ __forceinline__ double2 rot_rx(const double2 own, const double2 p, const double c, const double s) {
@@ -714,8 +718,13 @@ __device__ __forceinline__ void reg_gate_rx(const double cr, const double sr, do
   constexpr int B = 1 << J;
 #pragma unroll
   for (int k = 0; k < 16; ++k) if (!(k & B)) {
-    const double2 n0 = rot_rx(a[k], a[k | B], cr, sr), n1 = rot_rx(a[k | B], a[k], cr, sr);
-    a[k] = n0; a[k | B] = n1;
+    // rot_rx on both members of the pair, written so that every result can take its own operand's register: the four
+    // products first, then each FMA overwrites the component it read (same operations, same rounding as rot_rx)
+    double2& lo = a[k];
+    double2& hi = a[k | B];
+    const double t1 = __dmul_rn(sr, hi.y), t2 = __dmul_rn(sr, hi.x), t3 = __dmul_rn(sr, lo.y), t4 = __dmul_rn(sr, lo.x);
+    lo.x = __fma_rn(cr, lo.x, t1); lo.y = __fma_rn(cr, lo.y, -t2);
+    hi.x = __fma_rn(cr, hi.x, t3); hi.y = __fma_rn(cr, hi.y, -t4);
   }
 }
 // swap the pair where the control bit is set (same for both members: c != w)
