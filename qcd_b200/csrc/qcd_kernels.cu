@@ -678,11 +678,16 @@ struct RegMap {
   static constexpr size_t DYN_BYTES = XCHG_BYTES + TGT_BYTES;
 };
 
-struct __align__(16) RegStep { double cr, sr; int pk; int aux; };
-// pk: [2:0] kind [4:3] status [5] term [9:6] w [13:10] c [17:14] target position [21:18] control position [22] metric
-// needed whatever happens [27:23] opcode of the gate (ROP_*: ONE dispatch per step);  aux: [15:0] the 16 register slots
-// the CONTROL allows (all for P / RX, the slots with the control's register bit set for CP / CX, 0 = the control is a
-// thread bit: decided per thread) [27:16] wire mask
+struct __align__(16) RegStep { double cr, sr; int aux; int idx; int pk; int pad; };
+// Everything the step loop needs from an action, resolved by the decode-ahead so that the loop extracts no bit fields
+// it does not use:
+// pk:  [2:0] kind [4:3] status [5] term [22] metric needed whatever happens [27:23] opcode of the gate (ROP_*: ONE
+//      dispatch per step)
+// aux: [15:0] the 16 register slots the CONTROL allows (all of them unless the control is a register bit: then the slots
+//      with that bit set) [27:16] wire mask (1 << w | 1 << c)
+// idx: byte 0 = w, byte 1 = c (shuffle source lanes of the depth stack: the hardware takes them modulo 32), byte 2 = xor
+//      mask of the partner THREAD for a target on a lane / warp bit, byte 3 = the thread-index bits (tid) that must be set
+//      for the gate to act in this thread at all (thread-bit control; thread-bit target of a diagonal gate)
 //
 // Opcodes, resolved by the decode-ahead (they depend on the action alone): the target's register bit J and the
 // gate kind are compile-time in every case, and a CP between two register bits knows its four slots.
@@ -945,7 +950,7 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       // CP is symmetric in its two qubits: let the REGISTER-resident one play the target
       if (k.kind == K_CP && tpos >= 4 && cpos < 4) { const int x = tpos; tpos = cpos; cpos = x; }
       const bool controlled = k.kind == K_CP || k.kind == K_CX;
-      r.aux = (int)(!controlled ? 0xffffu : (cpos < 4 ? local_mask(cpos) : 0u)) | (((1 << k.w) | (1 << k.c)) << 16);
+      r.aux = (int)((controlled && cpos < 4) ? local_mask(cpos) : 0xffffu) | (((1 << k.w) | (1 << k.c)) << 16);
       // the ONE dispatch of the step loop: target register bit and gate kind (and a register-register CP's slot
       // set) become compile-time in the case bodies
       int op = ROP_NONE;
@@ -959,9 +964,13 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
           op = tpos < 9 ? ((k.kind == K_CX && cpos < 4) ? ROP_LANE_CX + cpos : ROP_LANE) : ROP_WARP;
         }
       }
+      // thread-index bits the gate needs set: a control on a thread bit; the target of a diagonal gate on a thread bit
+      const int tneed = ((controlled && cpos >= 4) ? 1 << (cpos - 4) : 0) | (op == ROP_DIAG_T ? 1 << (tpos - 4) : 0);
+      r.idx = k.w | (k.c << 8) | ((tpos >= 4 ? 1 << (tpos - 4) : 0) << 16) | (tneed << 24);
       // bit 22: the metric of this step is needed whatever happens (recorded / dense reward / last step)
-      r.pk = k.kind | (k.status << 3) | ((k.term ? 1 : 0) << 5) | (k.w << 6) | (k.c << 10) | (tpos << 14) | (cpos << 18) |
+      r.pk = k.kind | (k.status << 3) | ((k.term ? 1 : 0) << 5) |
              ((metric_every_step || t0 + i == T - 1) ? (1 << 22) : 0) | (op << 23);
+      r.pad = 0;
       s_tab[i] = r;
       if (k.status != QCD_ST_OK) atomicAdd(&s_nbad, 1);
     }
@@ -973,7 +982,8 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
 #pragma unroll 1
     for (int si = 0; si < nsteps; ++si) {
       const double cr = s_tab[si].cr, sr = s_tab[si].sr;
-      const int aux = s_tab[si].aux;
+      const int2 ai = *reinterpret_cast<const int2*>(&s_tab[si].aux);
+      const int aux = ai.x, idx = ai.y;
       const int pk = n_pk;
       n_pk = s_tab[si + 1].pk;                                 // (past the chunk's last step: never used; fetching the
                                                                // whole record ahead measured 2 % slower)
@@ -981,10 +991,9 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       // ---- QuantumCircuit.depth / count_ops / idle_wires (env.py:74,77,86): issued BEFORE the gate (independent of
       // it), so that the shuffle / REDUX latency hides behind the gate's arithmetic; consumed after it
       if (kind != K_NONE) {
-        const int w = (pk >> 6) & 15, c = (pk >> 10) & 15;
-        const int dw = __shfl_sync(FULL, d, w), dc = __shfl_sync(FULL, d, c);
+        const int dw = __shfl_sync(FULL, d, idx), dc = __shfl_sync(FULL, d, idx >> 8);   // (source lane modulo 32)
         const int lvl = min(max(dw, dc) + 1, 255);             // saturate (only past truncation)
-        if (lane == w || lane == c) d = lvl;
+        if (((unsigned)aux >> lane) & 0x10000u) d = lvl;       // lane == w || lane == c
         depth = max(depth, lvl);                               // the new level is the only counter that grew
         fresh = false;
         ops = min(ops + 1u, 0xffffu);
@@ -992,13 +1001,15 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
       }
 
       if (kind != K_NONE) {                                    // (Terminate / invalid action: no gate, no dispatch)
-        const int tpos = (pk >> 14) & 15, cpos = (pk >> 18) & 15;
-        // slots (of 16) this gate touches as far as the CONTROL is concerned (decoded ahead; 0 = thread-bit control)
-        unsigned cmask = (unsigned)aux & 0xffffu;
-        if (cmask == 0u) cmask = ((tpat >> cpos) & 1u) ? 0xffffu : 0u;
+        // does the gate act in this thread at all (thread-bit control / thread-bit target of a diagonal gate)?
+        const unsigned tneed = (unsigned)idx >> 24;
+        const bool pass = (~(unsigned)tid & tneed) == 0u;
+        // slots (of 16) this gate touches as far as the CONTROL is concerned
+        const unsigned cmask = pass ? (unsigned)aux & 0xffffu : 0u;
+        const int xm = (idx >> 16) & 0xff;                     // partner thread = tid ^ xm (lane / warp targets)
         switch ((pk >> 23) & 31) {
 #define QCD_ROP_J(J)                                                                        \
-          case ROP_P + J: if (cmask) reg_gate_p<J>(cr, sr, a); break;                          \
+          case ROP_P + J: if (pass) reg_gate_p<J>(cr, sr, a); break;                           \
           case ROP_RX + J: reg_gate_rx<J>(cr, sr, a); break;                                   \
           case ROP_CX + J: reg_gate_cx<J>(cmask, a); break;
           QCD_ROP_J(0) QCD_ROP_J(1) QCD_ROP_J(2) QCD_ROP_J(3)
@@ -1011,25 +1022,23 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
           case ROP_CP2 + cp2_index(2, 3): reg_gate_cp2<2, 3>(cr, sr, a); break;
           case ROP_DIAG_T:
             // diagonal, target (and for CP also the control) held by the thread index: all 16 slots or none
-            if (((tpat >> tpos) & 1u) && cmask) {
+            if (pass) {
 #pragma unroll
               for (int k = 0; k < A; ++k) a[k] = mul_phase(a[k], cr, sr);
             }
             break;
           case ROP_LANE: {                                     // partner = lane ^ xm: one shuffle per amplitude
-            const int xm = 1 << (tpos - 4);
 #pragma unroll
             for (int k = 0; k < A; ++k) {
               double2 p;
               p.x = __shfl_xor_sync(FULL, a[k].x, xm);
               p.y = __shfl_xor_sync(FULL, a[k].y, xm);
               if (kind == K_RX) a[k] = rot_rx(a[k], p, cr, sr);
-              else if ((cmask >> k) & 1u) a[k] = p;            // CX
+              else if (pass) a[k] = p;                         // CX whose control is a thread bit: all slots or none
             }
           } break;
 #define QCD_ROP_LANE_CX(J2)                                                                 \
           case ROP_LANE_CX + J2: {                                                             \
-            const int xm = 1 << (tpos - 4);                                                    \
             _Pragma("unroll") for (int k = 0; k < A; ++k) if (k & (1 << J2)) {                 \
               a[k].x = __shfl_xor_sync(FULL, a[k].x, xm);                                      \
               a[k].y = __shfl_xor_sync(FULL, a[k].y, xm);                                      \
@@ -1039,7 +1048,7 @@ replay_reg_kernel(const qcd_batch_t b, const void* __restrict__ actions, const i
 #undef QCD_ROP_LANE_CX
           case ROP_WARP:
             if (M::WARP_TARGETS) {                             // partner in another warp: through shared memory
-              const int ptid = tid ^ (1 << (tpos - 4));
+              const int ptid = tid ^ xm;
 #pragma unroll
               for (int k = 0; k < A; ++k) s_xchg[k * NT + tid] = a[k];
               __syncthreads();
